@@ -1,0 +1,114 @@
+// Internal kernel-argument structs and launcher prototypes (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "fnr_common.cuh"
+
+namespace fnr {
+
+struct KField {
+  int L, log2T, num_images;
+  int position_mode, appearance_mode, pass_semantic_gradients;
+  float scalings[FNR_MAX_LEVELS];
+  float aabb[6];
+};
+
+struct KParams {
+  float* hash_table;
+  float* base_w[FNR_MAX_LAYERS];
+  float* base_b[FNR_MAX_LAYERS];
+  float* sem_w[FNR_MAX_LAYERS];
+  float* sem_b[FNR_MAX_LAYERS];
+  float* head_w;
+  float* head_b;
+  float* col_w[FNR_MAX_LAYERS];
+  float* col_b[FNR_MAX_LAYERS];
+  float* app_embedding;
+};
+
+struct KRays {
+  int R, S;
+  const float* origins;
+  const float* directions;
+  const float* starts;
+  const float* ends;
+  const int32_t* camera_indices;
+};
+
+struct KFieldOut {
+  float* sample_density;
+  float* sample_rgb;
+  float* sample_semantics;
+  float* stash_encoding;
+};
+
+struct KComposite {
+  const float* sample_density;
+  const float* sample_rgb;
+  const float* sample_semantics;
+  float* rgb;
+  float* accumulation;
+  float* depth;
+  int32_t* depth_index;
+  float* semantics;
+  float* weights;
+  int clamp_rgb;
+};
+
+struct KCompositeBwd {
+  const float* weights;
+  const float* sample_density;
+  const float* sample_rgb;
+  const float* sample_semantics;
+  const float* accumulation;
+  const float* d_rgb;
+  const float* d_accumulation;
+  const float* d_semantics;
+  const float* d_weights;
+  const float* d_sample_density;
+  const float* d_sample_rgb;
+  const float* d_sample_semantics;
+  float* point_grads;  // [N,5]: d_density, d_rgb[3], d_logit
+  int pass_semantic_gradients;
+};
+
+struct KFieldBwd {
+  const float* point_grads;     // [N,5]
+  const float* stash_encoding;  // [N,32] or NULL (recompute)
+};
+
+struct KExport {
+  int B, S;
+  const float* origins;  // [B,3]
+  float normal[3];
+  const float* bins;  // [S+1] spacing bins in [0,1]
+  float near_plane, far_plane;
+  float logit_min, density_min, label_thr;
+  int capacity;
+  uint64_t point_base;
+  float* rows[3];
+  uint64_t* keys[3];
+  int32_t* counts;
+  float* sample_rgb;
+  float* point_location;
+  float* sample_semantics;
+  float* sample_density;
+  int64_t* semantics_colormap;
+};
+
+int sm_count();
+
+int launch_simt_field_forward(Family fam, const KField& F, const KParams& P, const KRays& Rr, const KFieldOut& O, cudaStream_t st);
+int launch_simt_composite(const KRays& Rr, const KComposite& Cm, cudaStream_t st);
+int launch_simt_composite_backward(const KRays& Rr, const KCompositeBwd& B, cudaStream_t st);
+int launch_simt_field_backward(Family fam, const KField& F, const KParams& P, const KParams& G, const KRays& Rr,
+                               const KFieldBwd& B, cudaStream_t st);
+int launch_simt_export(Family fam, const KField& F, const KParams& P, const KExport& E, cudaStream_t st);
+int launch_hash_indices(const KField& F, const KRays& Rr, int32_t* rows, float* positions, cudaStream_t st);
+
+// fused tcgen05 forward (fnr_tc.cu).  Returns FNR_ERR_UNSUPPORTED when the shape is not covered.
+bool tc_supported(Family fam, const KField& F, const KRays& Rr);
+int launch_tc_render_forward(Family fam, const KField& F, const KParams& P, const KRays& Rr, const KFieldOut& O,
+                             const KComposite& Cm, cudaStream_t st);
+
+}  // namespace fnr

@@ -1,0 +1,293 @@
+"""PyTorch-facing ops of the native hot path: thin autograd wrappers over the C ABI.
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); all arithmetic happens in
+libfruitnerf_b200.so.  Every op requires CUDA tensors and raises otherwise -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+
+
+@dataclass
+class FieldShape:
+    """Static shape of a FruitField as the kernels see it (fruit_nerf/fruit_field.py:70-166)."""
+
+    num_levels: int
+    features_per_level: int
+    log2_hashmap_size: int
+    scalings: Sequence[float]
+    geo_feat_dim: int
+    appearance_dim: int
+    num_images: int
+    base_dims: Sequence[int]
+    semantic_dims: Sequence[int]
+    color_dims: Sequence[int]
+    aabb: Sequence[float]  # 6 floats: min xyz, max xyz
+    pass_semantic_gradients: bool = False
+
+    def desc(self, position_mode: int, appearance_mode: int, impl: int = L.FNR_IMPL_AUTO) -> L.FieldDesc:
+        d = L.FieldDesc()
+        d.num_levels = self.num_levels
+        d.features_per_level = self.features_per_level
+        d.log2_hashmap_size = self.log2_hashmap_size
+        for i, s in enumerate(self.scalings):
+            d.scalings[i] = float(s)
+        d.geo_feat_dim = self.geo_feat_dim
+        d.appearance_dim = self.appearance_dim
+        d.num_images = self.num_images
+        for m, dims in ((d.base, self.base_dims), (d.semantic, self.semantic_dims), (d.color, self.color_dims)):
+            m.n_layers = len(dims) - 1
+            for i, v in enumerate(dims):
+                m.dims[i] = int(v)
+        for i, v in enumerate(self.aabb):
+            d.aabb[i] = float(v)
+        d.position_mode = position_mode
+        d.appearance_mode = appearance_mode
+        d.pass_semantic_gradients = int(self.pass_semantic_gradients)
+        d.impl = impl
+        return d
+
+    def param_layout(self) -> List[str]:
+        """Fixed order of the parameter tensors passed to the ops."""
+        names = ["hash_table"]
+        for pre, dims in (("base", self.base_dims), ("sem", self.semantic_dims)):
+            for i in range(len(dims) - 1):
+                names += [f"{pre}_w{i}", f"{pre}_b{i}"]
+        names += ["head_w", "head_b"]
+        for i in range(len(self.color_dims) - 1):
+            names += [f"col_w{i}", f"col_b{i}"]
+        names.append("app_embedding")
+        return names
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*ts: Optional[Tensor]) -> torch.device:
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise L.FruitNerfNativeError(
+                "fruitnerf_b200 ops need CUDA tensors: the hot path is hand-written sm_100a CUDA with no CPU fallback"
+            )
+        dev = t.device
+    return dev
+
+
+def _f32c(t: Tensor) -> Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _params_struct(shape: FieldShape, tensors: Sequence[Tensor]) -> L.FieldParams:
+    names = shape.param_layout()
+    assert len(names) == len(tensors), (len(names), len(tensors))
+    p = L.FieldParams()
+    for name, t in zip(names, tensors):
+        assert t.dtype == torch.float32 and t.is_contiguous(), name
+        if name in ("hash_table", "head_w", "head_b", "app_embedding"):
+            setattr(p, name, t.data_ptr())
+        else:
+            kind, idx = name[:-1], int(name[-1])  # e.g. base_w / 0
+            getattr(p, kind)[idx] = t.data_ptr()
+    return p
+
+
+def _stream(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def flat_zero_grads(tensors: Sequence[Tensor]) -> Tuple[Tensor, List[Tensor]]:
+    """One flat, zero-filled fp32 buffer with a 16-byte aligned view per parameter.  The backward
+    kernels accumulate straight into it; the multi-GPU path all-reduces it in one collective."""
+    offs, total = [], 0
+    for t in tensors:
+        offs.append(total)
+        total += (t.numel() + 3) // 4 * 4
+    flat = torch.zeros(total, dtype=torch.float32, device=tensors[0].device)
+    views = [flat[o : o + t.numel()].view_as(t) for o, t in zip(offs, tensors)]
+    return flat, views
+
+
+class _Render(torch.autograd.Function):
+    """Field forward (+ optional compositing) and its backward through the C ABI."""
+
+    @staticmethod
+    def forward(ctx, shape: FieldShape, mode: Dict, origins, directions, starts, ends, camera_indices, *params):
+        dev = _require_cuda(origins, directions, starts, ends, *params)
+        lib = L.load()
+        R, S = starts.shape[0], starts.shape[1]
+        origins, directions, starts, ends = map(_f32c, (origins, directions, starts, ends))
+        cam = None
+        if camera_indices is not None:
+            cam = camera_indices.reshape(-1).to(torch.int32).contiguous()
+        params = [p.detach() for p in params]
+        need_grad = any(ctx.needs_input_grad[7:])
+        composite = mode["composite"]
+        desc = shape.desc(mode["position_mode"], mode["appearance_mode"], mode.get("impl", L.FNR_IMPL_AUTO))
+        pstruct = _params_struct(shape, params)
+        rays = L.RayBatch(R, S, _ptr(origins), _ptr(directions), _ptr(starts), _ptr(ends), _ptr(cam))
+
+        f32 = dict(dtype=torch.float32, device=dev)
+        sd = torch.empty((R, S), **f32)
+        srgb = torch.empty((R, S, 3), **f32)
+        ssem = torch.empty((R, S), **f32)
+        stash = torch.empty((R, S, shape.num_levels * shape.features_per_level), **f32) if need_grad else None
+        if composite:
+            rgb = torch.empty((R, 3), **f32)
+            acc = torch.empty((R,), **f32)
+            depth = torch.empty((R,), **f32)
+            didx = torch.empty((R,), dtype=torch.int32, device=dev)
+            sem = torch.empty((R,), **f32)
+            w = torch.empty((R, S), **f32)
+        else:
+            rgb = acc = depth = didx = sem = w = None
+        out = L.RenderOut(_ptr(rgb), _ptr(acc), _ptr(depth), _ptr(didx), _ptr(sem), _ptr(w), _ptr(sd), _ptr(srgb),
+                          _ptr(ssem), _ptr(stash), int(mode.get("clamp_rgb", False)))
+        L.check(lib.fnr_render_forward(C.byref(desc), C.byref(pstruct), C.byref(rays), C.byref(out), _stream(dev)))
+
+        ctx.shape, ctx.mode = shape, mode
+        ctx.rs = (R, S)
+        ctx.saved = (origins, directions, starts, ends, cam, params, sd, srgb, ssem, stash, w, acc)
+        if composite:
+            ctx.mark_non_differentiable(depth, didx)
+            return rgb, acc, depth, didx, sem, w, sd, srgb, ssem
+        return sd, srgb, ssem
+
+    @staticmethod
+    def backward(ctx, *g):
+        lib = L.load()
+        shape, mode = ctx.shape, ctx.mode
+        origins, directions, starts, ends, cam, params, sd, srgb, ssem, stash, w, acc = ctx.saved
+        dev = sd.device
+        R, S = ctx.rs
+        if mode["composite"]:
+            g_rgb, g_acc, _, _, g_sem, g_w, g_sd, g_srgb, g_ssem = g
+        else:
+            g_sd, g_srgb, g_ssem = g
+            g_rgb = g_acc = g_sem = g_w = None
+        gs = [None if t is None else _f32c(t) for t in (g_rgb, g_acc, g_sem, g_w, g_sd, g_srgb, g_ssem)]
+        desc = shape.desc(mode["position_mode"], mode["appearance_mode"], L.FNR_IMPL_SIMT)
+        pstruct = _params_struct(shape, params)
+        flat, views = flat_zero_grads(params)
+        gstruct = _params_struct(shape, views)
+        rays = L.RayBatch(R, S, _ptr(origins), _ptr(directions), _ptr(starts), _ptr(ends), _ptr(cam))
+        saved = L.RenderSaved(_ptr(w), _ptr(sd), _ptr(srgb), _ptr(ssem), _ptr(stash), _ptr(acc))
+        up = L.RenderGrads(*[_ptr(t) for t in gs])
+        nbytes = C.c_size_t(0)
+        L.check(lib.fnr_render_backward_scratch_bytes(C.byref(desc), R, S, C.byref(nbytes)))
+        scratch = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        L.check(
+            lib.fnr_render_backward(C.byref(desc), C.byref(pstruct), C.byref(rays), C.byref(saved), C.byref(up),
+                                    C.byref(gstruct), scratch.data_ptr(), nbytes.value, _stream(dev))
+        )
+        _Render.last_flat_grad = flat
+        return (None, None, None, None, None, None, None, *views)
+
+    last_flat_grad: Optional[Tensor] = None
+
+
+def render(shape: FieldShape, params: Sequence[Tensor], origins: Tensor, directions: Tensor, starts: Tensor, ends: Tensor,
+           camera_indices: Optional[Tensor], position_mode: int, appearance_mode: int, clamp_rgb: bool = False,
+           impl: int = L.FNR_IMPL_AUTO) -> Dict[str, Tensor]:
+    """Fused FruitField.forward + get_weights + renderers (fruit_nerf/fruit_nerf.py:320-348).
+
+    origins/directions [R,3]; starts/ends [R,S]; camera_indices [R] or None.
+    """
+    mode = dict(composite=True, position_mode=position_mode, appearance_mode=appearance_mode, clamp_rgb=clamp_rgb, impl=impl)
+    rgb, acc, depth, didx, sem, w, sd, srgb, ssem = _Render.apply(shape, mode, origins, directions, starts, ends, camera_indices, *params)
+    return {
+        "rgb": rgb,
+        "accumulation": acc,
+        "depth": depth,
+        "depth_index": didx,
+        "semantics": sem,
+        "weights": w,
+        "sample_density": sd,
+        "sample_rgb": srgb,
+        "sample_semantics": ssem,
+    }
+
+
+def field(shape: FieldShape, params: Sequence[Tensor], origins: Tensor, directions: Tensor, starts: Tensor, ends: Tensor,
+          camera_indices: Optional[Tensor], position_mode: int, appearance_mode: int, impl: int = L.FNR_IMPL_AUTO):
+    """FruitField.forward (fruit_nerf/fruit_field.py:283-301): per-sample density, rgb, semantic logit."""
+    mode = dict(composite=False, position_mode=position_mode, appearance_mode=appearance_mode, impl=impl)
+    return _Render.apply(shape, mode, origins, directions, starts, ends, camera_indices, *params)
+
+
+def hash_indices(shape: FieldShape, origins, directions, starts, ends, position_mode: int):
+    """Hash-table rows [R,S,L,8] (nerfstudio corner order) and masked positions [R,S,3]."""
+    dev = _require_cuda(origins, directions, starts, ends)
+    lib = L.load()
+    R, S = starts.shape
+    origins, directions, starts, ends = map(_f32c, (origins, directions, starts, ends))
+    rows = torch.empty((R, S, shape.num_levels, 8), dtype=torch.int32, device=dev)
+    pos = torch.empty((R, S, 3), dtype=torch.float32, device=dev)
+    desc = shape.desc(position_mode, L.FNR_APP_ZEROS)
+    rays = L.RayBatch(R, S, _ptr(origins), _ptr(directions), _ptr(starts), _ptr(ends), None)
+    L.check(lib.fnr_hash_indices(C.byref(desc), C.byref(rays), rows.data_ptr(), pos.data_ptr(), _stream(dev)))
+    return rows, pos
+
+
+class ExportBuffers:
+    """Device-side compaction buffers of the volume export (three point sets, see include/)."""
+
+    def __init__(self, capacity: int, device, dense: bool = False):
+        self.capacity = capacity
+        self.rows = [torch.empty((capacity, 7), dtype=torch.float32, device=device) for _ in range(3)]
+        self.keys = [torch.empty((capacity,), dtype=torch.int64, device=device) for _ in range(3)]
+        self.counts = torch.zeros(3, dtype=torch.int32, device=device)
+        self.dense = dense
+
+
+def export_batch(shape: FieldShape, params: Sequence[Tensor], origins: Tensor, normal: Sequence[float], bins: Tensor,
+                 near: float, far: float, buffers: ExportBuffers, point_base: int = 0, dense_out: bool = False,
+                 thresholds=(3.0, 70.0, 0.9)) -> Optional[Dict[str, Tensor]]:
+    """One batch of FruitModel.get_export_outputs + the selection of sample_volume
+    (fruit_nerf/fruit_nerf.py:251-269; fruit_nerf/export/exporter_utils.py:100-153)."""
+    dev = _require_cuda(origins, bins, *params)
+    lib = L.load()
+    origins = _f32c(origins)
+    bins = _f32c(bins)
+    B, S = origins.shape[0], bins.numel() - 1
+    params = [p.detach() for p in params]
+    desc = shape.desc(L.FNR_POS_AABB, L.FNR_APP_MEAN)
+    pstruct = _params_struct(shape, params)
+    xp = L.ExportParams(float(thresholds[0]), float(thresholds[1]), float(thresholds[2]), buffers.capacity)
+    out = L.ExportOut()
+    for k in range(3):
+        out.rows[k] = buffers.rows[k].data_ptr()
+        out.keys[k] = buffers.keys[k].data_ptr()
+    out.counts = buffers.counts.data_ptr()
+    dense = None
+    if dense_out:
+        dense = {
+            "rgb": torch.empty((B, S, 3), dtype=torch.float32, device=dev),
+            "point_location": torch.empty((B, S, 3), dtype=torch.float32, device=dev),
+            "semantics": torch.empty((B, S), dtype=torch.float32, device=dev),
+            "density": torch.empty((B, S), dtype=torch.float32, device=dev),
+            "semantics_colormap": torch.empty((B, S), dtype=torch.int64, device=dev),
+        }
+        out.sample_rgb = dense["rgb"].data_ptr()
+        out.point_location = dense["point_location"].data_ptr()
+        out.sample_semantics = dense["semantics"].data_ptr()
+        out.sample_density = dense["density"].data_ptr()
+        out.semantics_colormap = dense["semantics_colormap"].data_ptr()
+    n3 = (C.c_float * 3)(*[float(v) for v in normal])
+    L.check(
+        lib.fnr_export_forward(C.byref(desc), C.byref(pstruct), origins.data_ptr(), n3, bins.data_ptr(), float(near),
+                               float(far), B, S, int(point_base), C.byref(xp), C.byref(out), _stream(dev))
+    )
+    return dense

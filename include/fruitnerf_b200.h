@@ -1,0 +1,210 @@
+/*
+ * fruitnerf_b200 -- C ABI of the B200-native FruitNeRF hot path.
+ *
+ * One shared library (libfruitnerf_b200.so, sm_100a) behind the reference's Nerfstudio plugin
+ * surface.  Plain C: no C++ or torch types cross this boundary.  Every buffer is a raw DEVICE
+ * pointer allocated and owned by the caller (PyTorch on the Python side); the library keeps no
+ * global state besides a thread-local error string.  All kernels are enqueued on the
+ * `cudaStream_t` passed as `void* stream` and never synchronise the host.
+ *
+ * Return value of every entry point: 0 = OK, negative = error (see FNR_ERR_*); the message is
+ * available from fnr_last_error().  No exceptions, no exit().
+ *
+ * Reference interfaces replaced (file:line under /root/reference):
+ *   fnr_render_forward   FruitModel.get_outputs after the sampler: FruitField.forward +
+ *                        RaySamples.get_weights + RGB/Depth/Accumulation/Semantic renderers
+ *                        (fruit_nerf/fruit_nerf.py:320-348; fruit_nerf/fruit_field.py:168-301)
+ *   fnr_render_backward  autograd of the above (the reference gets it from torch/tcnn autograd;
+ *                        loss inputs of fruit_nerf/fruit_nerf.py:359-366)
+ *   fnr_field_forward    FruitField.forward alone, per-sample RGB/SEMANTICS/DENSITY
+ *                        (fruit_nerf/fruit_field.py:283-301)
+ *   fnr_export_forward   FruitModel.get_export_outputs + the threshold/selection loop body of
+ *                        sample_volume (fruit_nerf/fruit_nerf.py:251-269;
+ *                        fruit_nerf/export/exporter_utils.py:100-153;
+ *                        fruit_nerf/components/ray_samplers.py:54-104)
+ */
+#ifndef FRUITNERF_B200_H
+#define FRUITNERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FNR_ABI_VERSION 1
+#define FNR_MAX_LEVELS 32
+#define FNR_MAX_LAYERS 4
+#define FNR_MAX_WIDTH 128
+
+#define FNR_OK 0
+#define FNR_ERR_INVALID_ARGUMENT (-1)
+#define FNR_ERR_UNSUPPORTED (-2)
+#define FNR_ERR_CUDA (-3)
+
+/* position_mode: how FruitField.get_density maps world positions to [0,1]^3
+ * (fruit_nerf/fruit_field.py:170-175). */
+#define FNR_POS_CONTRACT 0 /* (SceneContraction_inf(x) + 2) / 4  -- training / inference */
+#define FNR_POS_AABB 1     /* (x - aabb_min) / (aabb_max - aabb_min) -- export, after setup_inference */
+
+/* appearance_mode: which appearance embedding feeds the colour MLP
+ * (fruit_nerf/fruit_field.py:250-260, 217-219). */
+#define FNR_APP_PER_CAMERA 0 /* embedding[camera_index]  (self.training) */
+#define FNR_APP_MEAN 1       /* embedding.mean(0)        (inference/export, or use_average...) */
+#define FNR_APP_ZEROS 2      /* zeros                    (eval without average embedding) */
+
+/* implementation selector for the forward kernels */
+#define FNR_IMPL_AUTO 0    /* tcgen05 fused kernel when the shape is supported, else simt */
+#define FNR_IMPL_SIMT 1    /* fp32 CUDA-core kernels (exact-fp32 device reference) */
+#define FNR_IMPL_TCGEN05 2 /* fused tcgen05/TMEM kernel; FNR_ERR_UNSUPPORTED if shape unsupported */
+
+/* One nn.Linear stack: n_layers Linear layers, ReLU between them (nerfstudio MLP torch path);
+ * dims[0] = input width, dims[n_layers] = output width. */
+typedef struct fnr_mlp_desc {
+  int32_t n_layers;
+  int32_t dims[FNR_MAX_LAYERS + 1];
+} fnr_mlp_desc;
+
+/* Static description of a FruitField (fruit_nerf/fruit_field.py:70-166). */
+typedef struct fnr_field_desc {
+  int32_t num_levels;                /* L */
+  int32_t features_per_level;        /* F, must be 2 */
+  int32_t log2_hashmap_size;         /* T */
+  float scalings[FNR_MAX_LEVELS];    /* per-level scale, taken from the host module as is */
+  int32_t geo_feat_dim;              /* 15 / 30 */
+  int32_t appearance_dim;            /* 32 */
+  int32_t num_images;                /* rows of the appearance embedding */
+  fnr_mlp_desc base;                 /* L*F -> hidden -> 1+geo */
+  fnr_mlp_desc semantic;             /* geo -> ... -> sem_out (no output activation) */
+  fnr_mlp_desc color;                /* 16+geo+app -> ... -> 3, sigmoid */
+  float aabb[6];                     /* min xyz, max xyz (FNR_POS_AABB) */
+  int32_t position_mode;             /* FNR_POS_* */
+  int32_t appearance_mode;           /* FNR_APP_* */
+  int32_t pass_semantic_gradients;   /* 0: semantic MLP sees detach(geo), semantics use detach(w) */
+  int32_t impl;                      /* FNR_IMPL_* */
+} fnr_field_desc;
+
+/* fp32 device pointers in torch layouts (Linear weight = [out][in] row-major).  The same struct
+ * describes the gradient buffers for fnr_render_backward (all fields then writable, accumulated
+ * into with atomics: the caller zero-fills or pre-loads them). */
+typedef struct fnr_field_params {
+  float* hash_table;                 /* [L * 2^T, F] */
+  float* base_w[FNR_MAX_LAYERS];
+  float* base_b[FNR_MAX_LAYERS];
+  float* sem_w[FNR_MAX_LAYERS];
+  float* sem_b[FNR_MAX_LAYERS];
+  float* head_w;                     /* SemanticFieldHead Linear: [1][sem_out] */
+  float* head_b;                     /* [1] */
+  float* col_w[FNR_MAX_LAYERS];
+  float* col_b[FNR_MAX_LAYERS];
+  float* app_embedding;              /* [num_images][appearance_dim] */
+} fnr_field_params;
+
+/* A batch of R rays with S samples each (nerfstudio RaySamples after the sampler). */
+typedef struct fnr_ray_batch {
+  int32_t num_rays;                  /* R */
+  int32_t num_samples;               /* S */
+  const float* origins;              /* [R,3] */
+  const float* directions;           /* [R,3] */
+  const float* starts;               /* [R,S] frustum starts */
+  const float* ends;                 /* [R,S] frustum ends   */
+  const int32_t* camera_indices;     /* [R] or NULL (required for FNR_APP_PER_CAMERA) */
+} fnr_ray_batch;
+
+/* Outputs of the render forward.  Any pointer may be NULL to skip that output. */
+typedef struct fnr_render_out {
+  float* rgb;                        /* [R,3]  sum(w*c) + c_last*(1-sum w) */
+  float* accumulation;               /* [R]    sum w */
+  float* depth;                      /* [R]    median depth */
+  int32_t* depth_index;              /* [R]    median sample index (searchsorted left, clamped) */
+  float* semantics;                  /* [R]    sum(w * logit) */
+  float* weights;                    /* [R,S] */
+  float* sample_density;             /* [R,S]   field outputs per sample ... */
+  float* sample_rgb;                 /* [R,S,3] */
+  float* sample_semantics;           /* [R,S]   (logit) */
+  float* stash_encoding;             /* [R,S,L*F] encoded features kept for the backward, or NULL */
+  int32_t clamp_rgb;                 /* 1: eval-mode RGBRenderer (nan_to_num + clamp to [0,1]) */
+} fnr_render_out;
+
+/* Gradients flowing into the render backward.  NULL = zero. */
+typedef struct fnr_render_grads {
+  const float* d_rgb;                /* [R,3] */
+  const float* d_accumulation;       /* [R]   */
+  const float* d_semantics;          /* [R]   */
+  const float* d_weights;            /* [R,S] */
+  const float* d_sample_density;     /* [R,S]   direct per-sample grads (FruitField.forward users) */
+  const float* d_sample_rgb;         /* [R,S,3] */
+  const float* d_sample_semantics;   /* [R,S]   */
+} fnr_render_grads;
+
+/* Forward products the backward re-reads (written by fnr_render_forward). */
+typedef struct fnr_render_saved {
+  const float* weights;              /* [R,S] */
+  const float* sample_density;       /* [R,S] */
+  const float* sample_rgb;           /* [R,S,3] */
+  const float* sample_semantics;     /* [R,S] */
+  const float* stash_encoding;       /* [R,S,L*F] */
+  const float* accumulation;         /* [R] */
+} fnr_render_saved;
+
+/* Export: thresholds and compacted outputs of sample_volume's loop body
+ * (fruit_nerf/export/exporter_utils.py:111-153). */
+typedef struct fnr_export_params {
+  float semantic_logit_min;          /* 3.0   : mask_sem  = logit   >= 3    */
+  float density_min;                 /* 70.0  : mask_den  = density >= 70   */
+  float label_sigmoid_threshold;     /* 0.9   : label = heaviside(sigmoid(logit) - 0.9) */
+  int32_t capacity;                  /* rows available in each of the three output sets */
+} fnr_export_params;
+
+typedef struct fnr_export_out {
+  /* set 0: label & density ("semantic_colormap"), set 1: logit & density ("semantic"),
+   * set 2: density only ("density").  Each row: x y z r g b a, a = sigmoid(logit) for sets 0/1
+   * and sigmoid(density) for set 2.  counts[3] are device counters the caller zeroes before the
+   * first batch; rows beyond capacity are counted but not written. */
+  float* rows[3];                    /* [capacity,7] each */
+  uint64_t* keys[3];                 /* [capacity] global point index (ray*S+sample) of each row, or NULL */
+  int32_t* counts;                   /* [3] */
+  /* optional dense per-point outputs (get_export_outputs), NULL to skip */
+  float* sample_rgb;                 /* [B,S,3] */
+  float* point_location;             /* [B,S,3] */
+  float* sample_semantics;           /* [B,S] */
+  float* sample_density;             /* [B,S] */
+  int64_t* semantics_colormap;       /* [B,S] label in {0,1} */
+} fnr_export_out;
+
+int fnr_version(void);
+const char* fnr_last_error(void);
+
+/* FruitModel.get_outputs minus the sampler: field + compositing, fused. */
+int fnr_render_forward(const fnr_field_desc* desc, const fnr_field_params* params, const fnr_ray_batch* rays,
+                       const fnr_render_out* out, void* stream);
+
+/* Gradients of fnr_render_forward w.r.t. every field parameter, accumulated into `grads`. */
+int fnr_render_backward(const fnr_field_desc* desc, const fnr_field_params* params, const fnr_ray_batch* rays,
+                        const fnr_render_saved* saved, const fnr_render_grads* upstream,
+                        const fnr_field_params* grads, void* scratch, size_t scratch_bytes, void* stream);
+
+/* Bytes of caller-allocated device scratch fnr_render_backward needs for this shape. */
+int fnr_render_backward_scratch_bytes(const fnr_field_desc* desc, int32_t num_rays, int32_t num_samples, size_t* bytes);
+
+/* Uniform-volume export of one ray batch: rays are `origins[b] + t * normal` (normal = 3 HOST
+ * floats), sample s spans t in [bins[s], bins[s+1]] * far + (1 - bins) * near where `bins` is a
+ * DEVICE array of S+1 spacing bins in [0,1] (the reference builds it with torch.linspace on the
+ * host, components/ray_samplers.py:75; the caller does the same so the bits agree).  The field
+ * runs in FNR_POS_AABB / FNR_APP_MEAN mode.  `point_base` is the global index of this batch's
+ * first point (for `keys`). */
+int fnr_export_forward(const fnr_field_desc* desc, const fnr_field_params* params, const float* origins,
+                       const float* normal, const float* bins, float near_plane, float far_plane,
+                       int32_t num_rays, int32_t num_samples, uint64_t point_base,
+                       const fnr_export_params* xp, const fnr_export_out* out, void* stream);
+
+/* Hash-grid row indices (exact-integer parity hook): rows[N,L,8] in nerfstudio corner order for
+ * the masked [0,1]^3 positions of the given samples; also writes positions[N,3] if non-NULL. */
+int fnr_hash_indices(const fnr_field_desc* desc, const fnr_ray_batch* rays, int32_t* rows, float* positions,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRUITNERF_B200_H */

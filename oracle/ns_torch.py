@@ -1,0 +1,289 @@
+"""Restatement of the nerfstudio-0.3.2 *torch-fallback* components FruitNeRF's hot path calls.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY UNPINNED: nerfstudio is absent from this
+image and from /root/reference; each function names the reference call site whose behaviour it
+restates and the [NS] class it stands in for.  All arithmetic is fp32 on the CPU, written as
+separate elementwise torch ops (no fused multiply-add), which is what the CUDA path's
+index-defining arithmetic reproduces bit-for-bit.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor
+
+HASH_PRIMES = (1, 2654435761, 805459861)  # [NS] HashEncoding.hash_fn multipliers
+
+
+# --------------------------------------------------------------------------------------
+# Hash-grid encoding            (reference ctor call: fruit_nerf/fruit_field.py:124-131)
+# --------------------------------------------------------------------------------------
+def hash_scalings(num_levels: int, min_res: int, max_res: int) -> Tensor:
+    """[NS] HashEncoding.__init__: ``floor(min_res * growth**levels)``.
+
+    ``growth`` is a numpy float64, ``levels`` an int64 tensor: ``np.float64 ** Tensor`` defers to
+    ``Tensor.__rpow__`` and evaluates in float32 -- the top level of max_res=2048 is 2047, not
+    2048 (SURVEY.md section 7 "float-fragile").  Restated with the very same expression so the
+    values are whatever torch produces; the CUDA path receives this array and never recomputes it.
+    """
+    levels = torch.arange(num_levels)
+    growth = np.exp((np.log(max_res) - np.log(min_res)) / (num_levels - 1)) if num_levels > 1 else 1
+    return torch.floor(min_res * growth**levels).to(torch.float32)
+
+
+def hash_fn(coords: Tensor, log2_hashmap_size: int, num_levels: int) -> Tensor:
+    """[NS] HashEncoding.hash_fn.  coords: int32 [..., L, 3] -> int64 table row [..., L].
+
+    int32 * int64 promotes to int64; xor and ``% 2**T`` only look at the low T bits, so this is
+    identical to uint32 wrap-around arithmetic (what the kernel does) for T <= 32.
+    """
+    t = coords * torch.tensor(HASH_PRIMES, dtype=torch.int64)
+    x = torch.bitwise_xor(t[..., 0], t[..., 1])
+    x = torch.bitwise_xor(x, t[..., 2])
+    x = x % (2**log2_hashmap_size)
+    x = x + torch.arange(num_levels, dtype=torch.int64) * (2**log2_hashmap_size)
+    return x
+
+
+def hash_corner_indices(p: Tensor, scalings: Tensor, log2_hashmap_size: int) -> Tuple[Tensor, Tensor]:
+    """Corner rows and trilinear offsets of [NS] HashEncoding.pytorch_fwd.
+
+    p: [N,3] in [0,1].  Returns (idx [N,L,8] int64 in the [NS] corner order 0..7, offset [N,L,3]).
+    Corner order (c = ceil, f = floor): 0 ccc, 1 cfc, 2 ffc, 3 fcc, 4 ccf, 5 cff, 6 fff, 7 fcf.
+    """
+    L = scalings.numel()
+    scaled = p[..., None, :] * scalings.view(-1, 1)  # [N, L, 3]
+    c = torch.ceil(scaled).type(torch.int32)
+    f = torch.floor(scaled).type(torch.int32)
+    offset = scaled - f
+
+    def pick(sel: str) -> Tensor:
+        parts = [(c if s == "c" else f)[..., i : i + 1] for i, s in enumerate(sel)]
+        return hash_fn(torch.cat(parts, dim=-1), log2_hashmap_size, L)
+
+    order = ("ccc", "cfc", "ffc", "fcc", "ccf", "cff", "fff", "fcf")
+    idx = torch.stack([pick(s) for s in order], dim=-1)  # [N, L, 8]
+    return idx, offset
+
+
+def hash_encode(p: Tensor, table: Tensor, scalings: Tensor, log2_hashmap_size: int) -> Tensor:
+    """[NS] HashEncoding.pytorch_fwd: [N,3] -> [N, L*F], level-major."""
+    idx, offset = hash_corner_indices(p, scalings, log2_hashmap_size)
+    f = [table[idx[..., k]] for k in range(8)]  # each [N, L, F]
+    ox, oy, oz = offset[..., 0:1], offset[..., 1:2], offset[..., 2:3]
+    f_03 = f[0] * ox + f[3] * (1 - ox)
+    f_12 = f[1] * ox + f[2] * (1 - ox)
+    f_56 = f[5] * ox + f[6] * (1 - ox)
+    f_47 = f[4] * ox + f[7] * (1 - ox)
+    f0312 = f_03 * oy + f_12 * (1 - oy)
+    f4756 = f_47 * oy + f_56 * (1 - oy)
+    enc = f0312 * oz + f4756 * (1 - oz)
+    return torch.flatten(enc, start_dim=-2, end_dim=-1)
+
+
+# --------------------------------------------------------------------------------------
+# MLP / heads / activations     (fruit_field.py:132-166; components/field_heads.py:29-40)
+# --------------------------------------------------------------------------------------
+def mlp_forward(x: Tensor, weights: Sequence[Tensor], biases: Sequence[Tensor], out_activation: Optional[str] = None) -> Tensor:
+    """[NS] MLP.pytorch_fwd without skip connections: Linear(+bias) layers, ReLU between."""
+    n = len(weights)
+    for i, (w, b) in enumerate(zip(weights, biases)):
+        x = torch.nn.functional.linear(x, w, b)
+        if i < n - 1:
+            x = torch.relu(x)
+    if out_activation == "sigmoid":
+        x = torch.sigmoid(x)
+    elif out_activation is not None:
+        raise ValueError(out_activation)
+    return x
+
+
+class _TruncExp(torch.autograd.Function):
+    """[NS] field_components.activations.trunc_exp (fruit_field.py:191): exp forward,
+    ``g * exp(clamp(x, -15, 15))`` backward."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return torch.exp(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return g * torch.exp(x.clamp(-15, 15))
+
+
+trunc_exp = _TruncExp.apply
+
+
+def sh_degree4(d: Tensor) -> Tensor:
+    """[NS] SHEncoding(levels=4).pytorch_fwd = components_from_spherical_harmonics(4, d).
+
+    FruitField passes ``shift_directions_for_tcnn(d) = (d+1)/2`` (fruit_field.py:208,243) and the
+    torch fallback evaluates the basis on that shifted vector as given -- restated literally.
+    """
+    x, y, z = d[..., 0], d[..., 1], d[..., 2]
+    xx, yy, zz = x**2, y**2, z**2
+    c = torch.zeros((*d.shape[:-1], 16), dtype=d.dtype)
+    c[..., 0] = 0.28209479177387814
+    c[..., 1] = 0.4886025119029199 * y
+    c[..., 2] = 0.4886025119029199 * z
+    c[..., 3] = 0.4886025119029199 * x
+    c[..., 4] = 1.0925484305920792 * x * y
+    c[..., 5] = 1.0925484305920792 * y * z
+    c[..., 6] = 0.9461746957575601 * zz - 0.31539156525251999
+    c[..., 7] = 1.0925484305920792 * x * z
+    c[..., 8] = 0.5462742152960396 * (xx - yy)
+    c[..., 9] = 0.5900435899266435 * y * (3 * xx - yy)
+    c[..., 10] = 2.890611442640554 * x * y * z
+    c[..., 11] = 0.4570457994644658 * y * (5 * zz - 1)
+    c[..., 12] = 0.3731763325901154 * z * (5 * zz - 3)
+    c[..., 13] = 0.4570457994644658 * x * (5 * zz - 1)
+    c[..., 14] = 1.445305721320277 * z * (xx - yy)
+    c[..., 15] = 0.5900435899266435 * x * (xx - 3 * yy)
+    return c
+
+
+# --------------------------------------------------------------------------------------
+# Positions                     (fruit_field.py:170-179)
+# --------------------------------------------------------------------------------------
+def frustum_positions(origins: Tensor, directions: Tensor, starts: Tensor, ends: Tensor) -> Tensor:
+    """[NS] Frustums.get_positions: ``o + d * (start + end) / 2`` in that op order."""
+    return origins + directions * (starts + ends) / 2
+
+
+def scene_contraction_inf(x: Tensor) -> Tensor:
+    """[NS] SceneContraction(order=inf) (fruit_nerf.py:85): x if |x|inf < 1 else (2 - 1/m) * (x/m)."""
+    mag = torch.linalg.norm(x, ord=float("inf"), dim=-1)[..., None]
+    return torch.where(mag < 1, x, (2 - (1 / mag)) * (x / mag))
+
+
+def normalized_positions(x: Tensor, aabb: Tensor) -> Tensor:
+    """[NS] SceneBox.get_normalized_positions (fruit_field.py:175): (x - aabb[0]) / (aabb[1]-aabb[0])."""
+    lengths = aabb[1] - aabb[0]
+    return (x - aabb[0]) / lengths
+
+
+# --------------------------------------------------------------------------------------
+# Compositing                   (fruit_nerf.py:325-348)
+# --------------------------------------------------------------------------------------
+def get_weights(deltas: Tensor, densities: Tensor) -> Tensor:
+    """[NS] RaySamples.get_weights (fruit_nerf.py:325).  deltas, densities: [R,S,1]."""
+    delta_density = deltas * densities
+    alphas = 1 - torch.exp(-delta_density)
+    transmittance = torch.cumsum(delta_density[..., :-1, :], dim=-2)
+    transmittance = torch.cat([torch.zeros((*transmittance.shape[:1], 1, 1)), transmittance], dim=-2)
+    transmittance = torch.exp(-transmittance)
+    weights = alphas * transmittance
+    return torch.nan_to_num(weights)
+
+
+def render_rgb_last_sample(rgb: Tensor, weights: Tensor, training: bool) -> Tensor:
+    """[NS] RGBRenderer(background_color="last_sample") (fruit_nerf.py:164,329)."""
+    if not training:
+        rgb = torch.nan_to_num(rgb)
+    comp = torch.sum(weights * rgb, dim=-2)
+    acc = torch.sum(weights, dim=-2)
+    background = rgb[..., -1, :]
+    comp = comp + background * (1.0 - acc)
+    if not training:
+        comp = torch.clamp(comp, min=0.0, max=1.0)
+    return comp
+
+
+def render_accumulation(weights: Tensor) -> Tensor:
+    """[NS] AccumulationRenderer (fruit_nerf.py:331)."""
+    return torch.sum(weights, dim=-2)
+
+
+def render_depth_median(weights: Tensor, starts: Tensor, ends: Tensor) -> Tuple[Tensor, Tensor]:
+    """[NS] DepthRenderer(method="median") (fruit_nerf.py:330).  Returns (depth [R,1], index [R,1])."""
+    steps = (starts + ends) / 2
+    cumulative = torch.cumsum(weights[..., 0], dim=-1)
+    split = torch.ones((*weights.shape[:-2], 1)) * 0.5
+    idx = torch.searchsorted(cumulative, split, side="left")
+    idx = torch.clamp(idx, 0, steps.shape[-2] - 1)
+    return torch.gather(steps[..., 0], dim=-1, index=idx), idx
+
+
+def render_semantics(semantics: Tensor, weights: Tensor) -> Tensor:
+    """[NS] SemanticRenderer (fruit_nerf.py:346-348): sum(w * logits)."""
+    return torch.sum(weights * semantics, dim=-2)
+
+
+# --------------------------------------------------------------------------------------
+# Export sampling               (components/ray_samplers.py:54-104, ray_generators.py:46-66,
+#                                data/fruit_datamanager.py:42-121)
+# --------------------------------------------------------------------------------------
+def uniform_bins(nears: Tensor, fars: Tensor, num_samples: int) -> Tuple[Tensor, Tensor]:
+    """UniformSamplerWithNoise.generate_ray_samples in eval mode (no jitter; export runs under
+    model.eval()).  nears/fars [B,1] -> (starts [B,S,1], ends [B,S,1])."""
+    bins = torch.linspace(0.0, 1.0, num_samples + 1)[None, ...]
+    euclid = bins * fars + (1 - bins) * nears  # spacing_fn = identity
+    return euclid[..., :-1, None], euclid[..., 1:, None]
+
+
+def aabb_corners(aabb) -> Tensor:
+    """get_corners_of_aabb (fruit_datamanager.py:42-68)."""
+    mn, mx = aabb[0], aabb[1]
+    return torch.tensor(
+        [
+            [mn[0], mn[1], mn[2]],
+            [mx[0], mn[1], mn[2]],
+            [mn[0], mx[1], mn[2]],
+            [mx[0], mx[1], mn[2]],
+            [mn[0], mn[1], mx[2]],
+            [mx[0], mn[1], mx[2]],
+            [mn[0], mx[1], mx[2]],
+            [mx[0], mx[1], mx[2]],
+        ],
+        dtype=torch.float32,
+    )
+
+
+def surface_points(aabb, n: int) -> Tuple[Tensor, Tensor]:
+    """sample_surface_points (fruit_datamanager.py:71-121) on the 8 corners of ``aabb``.
+
+    Returns (points [nx*ny, 3] x-major, plane_vector [1,3])."""
+    corners = aabb_corners(aabb)
+    c1, c2, c3 = corners[0], corners[1], corners[2]
+    dxyz = torch.abs(torch.max(corners, dim=0).values - torch.min(corners, dim=0).values)
+    const_axis = int(torch.argmax(torch.logical_and(c1 == c2, c2 == c3).to(int)))
+    ax = torch.argmax(torch.abs(c1 - c2))
+    x = torch.linspace(float(c1[ax]), float(c2[ax]), int(dxyz[0] / dxyz[const_axis] * n), dtype=torch.float32)
+    ay = torch.argmax(torch.abs(c1 - c3))
+    y = torch.linspace(float(c1[ay]), float(c3[ay]), int(dxyz[1] / dxyz[const_axis] * n), dtype=torch.float32)
+    xx, yy = torch.meshgrid(x, y, indexing="ij")
+    pts = torch.column_stack((xx.flatten(), yy.flatten(), torch.full_like(xx.flatten(), float(c3[const_axis]))))
+    c4 = corners[-1]
+    plane = torch.tensor(
+        [[0, 0, float(torch.sign(c4[const_axis]) * torch.abs(c1[const_axis]) + torch.abs(c4[const_axis]))]],
+        dtype=torch.float32,
+    )
+    return pts, plane
+
+
+def orthographic_rays(points: Tensor, plane_vector: Tensor, batch: int, count: int):
+    """OrthographicRayGenerator.forward (ray_generators.py:46-66); ``count`` is 1-based."""
+    start, end = batch * (count - 1), batch * count
+    if batch * count >= points.shape[0]:
+        end = points.shape[0]
+    normal = torch.nn.functional.normalize(plane_vector)
+    norm = torch.linalg.norm(plane_vector)
+    o = points[start:end]
+    n = o.shape[0]
+    return o, normal.repeat(n, 1), torch.zeros(n, 1), torch.ones(n, 1) * norm
+
+
+# --------------------------------------------------------------------------------------
+# Losses                        (fruit_nerf.py:359-372)
+# --------------------------------------------------------------------------------------
+def rgb_mse(image: Tensor, rgb: Tensor) -> Tensor:
+    return torch.nn.functional.mse_loss(image, rgb)
+
+
+def semantic_bce(logits: Tensor, mask: Tensor) -> Tensor:
+    return torch.nn.functional.binary_cross_entropy_with_logits(logits, mask, reduction="mean")

@@ -1,0 +1,215 @@
+"""CPU tests of the oracle: golden vectors + independent known-answer checks.
+
+The reference has no tests of its own, so the known answers below are derived by
+hand / by independent integer arithmetic from the formulas the reference's dependencies publish.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from fruitnerf_b200 import synthetic as syn
+from oracle import fruit_ref as fr
+from oracle import ns_torch as ns
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def test_scalings_are_float32_floor():
+    # float32 pow through Tensor.__rpow__: top level of max_res 2048 is 2047
+    assert ns.hash_scalings(16, 16, 2048).tolist() == [16, 22, 30, 42, 58, 80, 111, 153, 212, 294, 406, 561, 776, 1072, 1482, 2047]
+    assert ns.hash_scalings(16, 16, 4096)[-1] == 4095
+
+
+def _py_hash(x, y, z, T, level):
+    return (((x * 1) ^ (y * 2654435761) ^ (z * 805459861)) % (2**T)) + level * 2**T
+
+
+@pytest.mark.parametrize("T,max_res", [(17, 2048), (19, 2048), (21, 4096)])
+def test_hash_rows_against_python_ints_and_golden(T, max_res):
+    g = np.load(GOLD / "hash_indices.npz")
+    pts = torch.from_numpy(g["points"])
+    scal = ns.hash_scalings(16, 16, max_res)
+    idx, off = ns.hash_corner_indices(pts, scal, T)
+    assert np.array_equal(idx.numpy(), g[f"idx_T{T}"])
+    assert np.array_equal(off.numpy(), g[f"off_T{T}"])
+    # independent arbitrary-precision check + uint32 wrap-around equivalence
+    order = ("ccc", "cfc", "ffc", "fcc", "ccf", "cff", "fff", "fcf")
+    for n in range(pts.shape[0]):
+        for l in range(16):
+            s = (pts[n] * scal[l]).numpy()
+            f, c = np.floor(s).astype(np.int64), np.ceil(s).astype(np.int64)
+            for k, sel in enumerate(order):
+                v = [int(c[i]) if ch == "c" else int(f[i]) for i, ch in enumerate(sel)]
+                assert int(idx[n, l, k]) == _py_hash(*v, T, l)
+                u32 = ((v[0] & 0xFFFFFFFF) ^ ((v[1] * 2654435761) & 0xFFFFFFFF) ^ ((v[2] * 805459861) & 0xFFFFFFFF)) & (2**T - 1)
+                assert int(idx[n, l, k]) == u32 + l * 2**T
+
+
+def test_hash_encode_is_trilinear_interpolation():
+    """On a table that stores an affine function of the corner coordinates the encoding must
+    reproduce that function at the query point (trilinear interpolation reproduces affine maps)."""
+    T, L = 14, 2
+    scal = torch.tensor([4.0, 7.0])
+    table = torch.zeros(L * 2**T, 2)
+    # fill every reachable corner of both levels
+    for l, res in enumerate((4, 7)):
+        g = torch.arange(res + 1)
+        xyz = torch.stack(torch.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+        rows = ns.hash_fn(xyz[:, None, :].expand(-1, L, 3).to(torch.int32), T, L)[:, l]
+        assert rows.unique().numel() == rows.numel(), "test needs a collision-free table"
+        vals = xyz.float() / res
+        table[rows, 0] = 1.0 + 2.0 * vals[:, 0] - 3.0 * vals[:, 1] + 0.5 * vals[:, 2]
+        table[rows, 1] = vals[:, 2]
+    p = torch.tensor([[0.3, 0.6, 0.9], [0.01, 0.5, 0.25], [0.5, 0.5, 0.5]])
+    enc = ns.hash_encode(p, table, scal, T)
+    want0 = 1.0 + 2.0 * p[:, 0] - 3.0 * p[:, 1] + 0.5 * p[:, 2]
+    for l in range(L):
+        assert torch.allclose(enc[:, 2 * l], want0, atol=1e-5)
+        assert torch.allclose(enc[:, 2 * l + 1], p[:, 2], atol=1e-6)
+
+
+def test_contraction_and_masking():
+    x = torch.tensor([[0.5, -0.25, 0.0], [2.0, 0.0, 0.0], [0.0, -4.0, 2.0]])
+    c = ns.scene_contraction_inf(x)
+    assert torch.allclose(c[0], x[0])
+    assert torch.allclose(c[1], torch.tensor([1.5, 0.0, 0.0]))
+    assert torch.allclose(c[2], torch.tensor([0.0, -1.75, 0.875]))
+    aabb = torch.tensor([[-1.0, -1, -1], [1, 1, 1]])
+    pos, sel = fr.sample_positions(torch.tensor([[[0.0, 0, 0]], [[5.0, 0, 0]]]), torch.tensor([[[1.0, 0, 0]], [[1.0, 0, 0]]]),
+                                   torch.tensor([[[0.0]], [[0.0]]]), torch.tensor([[[1.0]], [[1.0]]]), aabb, contraction=False)
+    assert sel.tolist() == [[True], [False]] and pos[1].abs().sum() == 0
+    assert torch.allclose(pos[0], torch.tensor([[0.75, 0.5, 0.5]]))
+
+
+def test_sh_degree4_known_values():
+    c = ns.sh_degree4(torch.tensor([[0.0, 0.0, 1.0], [1.0, 0.0, 0.0]]))
+    assert torch.allclose(c[:, 0], torch.full((2,), 0.28209479))
+    assert abs(float(c[0, 6]) - (0.9461746957575601 - 0.31539156525251999)) < 1e-6
+    assert abs(float(c[0, 12]) - 0.3731763325901154 * 2) < 1e-6
+    assert abs(float(c[1, 15]) - 0.5900435899266435) < 1e-6 and abs(float(c[1, 3]) - 0.4886025119029199) < 1e-6
+
+
+def test_compositing_known_answers():
+    deltas = torch.full((4, 3, 1), 0.5)
+    dens = torch.tensor([[0.0, 0.0, 0.0], [1e9, 0.0, 0.0], [2.0, 2.0, 2.0], [float("nan"), 1.0, 1.0]])[..., None]
+    w = ns.get_weights(deltas, dens)
+    assert w[0].abs().sum() == 0  # empty space
+    assert torch.allclose(w[1, :, 0], torch.tensor([1.0, 0.0, 0.0]))  # opaque first sample
+    a = 1 - np.exp(-1.0)
+    assert torch.allclose(w[2, :, 0], torch.tensor([a, a * np.exp(-1.0), a * np.exp(-2.0)], dtype=torch.float32), atol=1e-6)
+    assert torch.isfinite(w[3]).all() and w[3, 0, 0] == 0  # nan_to_num
+    rgb = torch.tensor([[[1.0, 0, 0], [0, 1.0, 0], [0, 0, 1.0]]]).repeat(4, 1, 1)
+    out = ns.render_rgb_last_sample(rgb, w, training=True)
+    assert torch.allclose(out[0], torch.tensor([0.0, 0.0, 1.0]))  # background = last sample colour
+    assert torch.allclose(out[1], torch.tensor([1.0, 0.0, 0.0]))
+    starts = torch.tensor([0.0, 0.5, 1.0]).view(1, 3, 1).repeat(4, 1, 1)
+    depth, idx = ns.render_depth_median(w, starts, starts + 0.5)
+    assert idx[:3, 0].tolist() == [2, 0, 0]  # never reaches 0.5 -> clamped to the last sample
+    assert float(depth[2]) == 0.25
+    # exact tie: cumulative weight hits 0.5 exactly at index 1 (searchsorted side="left")
+    wt = torch.tensor([[[0.25], [0.25], [0.25]]])
+    _, it = ns.render_depth_median(wt, starts[:1], starts[:1] + 0.5)
+    assert int(it) == 1
+
+
+def test_trunc_exp_gradient_is_clamped():
+    x = torch.tensor([-20.0, 0.0, 20.0], requires_grad=True)
+    ns.trunc_exp(x).sum().backward()
+    assert torch.allclose(x.grad, torch.exp(torch.tensor([-15.0, 0.0, 15.0])))
+
+
+def test_export_thresholds_and_selection():
+    out = {
+        "point_location": torch.arange(18.0).view(1, 6, 3),
+        "semantics": torch.tensor([[2.9, 3.0, 5.0, 5.0, 2.0, 2.2]]),
+        "density": torch.tensor([[100.0, 69.9, 70.0, 10.0, 80.0, 75.0]]),
+        "rgb": torch.rand(1, 6, 3),
+    }
+    out["semantics_colormap"] = torch.heaviside(torch.sigmoid(out["semantics"]) - 0.9, torch.tensor(0.0)).long()
+    assert out["semantics_colormap"].tolist() == [[1, 1, 1, 1, 0, 1]]  # sigmoid(2.2) = 0.9002 > 0.9
+    sel = fr.export_select(out)
+    assert sel["density"]["points"].shape[0] == 4
+    assert sel["semantic"]["points"][:, 0].tolist() == [6.0]  # logit >= 3 and density >= 70
+    assert sel["semantic_colormap"]["points"][:, 0].tolist() == [0.0, 6.0, 15.0]
+    assert torch.allclose(sel["semantic"]["colors"][:, 3], torch.sigmoid(torch.tensor([5.0])))
+    assert torch.allclose(sel["density"]["colors"][:, 3], torch.ones(4))  # sigmoid(density >= 70) == 1
+
+
+def test_export_grid_golden_and_shapes():
+    g = np.load(GOLD / "export_grid.npz")
+    for n, aabb, tag in ((4, ((-1, -1, -1), (1, 1, 1)), "n4_cube"), (64, ((-1, -1, -1), (1, 1, 1)), "n64_cube"),
+                         (10, ((-1.0, -0.5, -0.25), (1.0, 0.5, 0.75)), "n10_box")):
+        pts, plane = ns.surface_points(aabb, n)
+        assert np.array_equal(pts.numpy(), g[f"{tag}_points"]) and np.array_equal(plane.numpy(), g[f"{tag}_plane"])
+    pts, plane = ns.surface_points(((-1.0, -0.5, -0.25), (1.0, 0.5, 0.75)), 10)
+    assert pts.shape == (int(2.0 / 1.0 * 10) * int(1.0 / 1.0 * 10), 3)  # int(dx/dz*n) x int(dy/dz*n), fruit_datamanager.py:100-103
+    assert torch.all(pts[:, 2] == -0.25) and torch.allclose(plane, torch.tensor([[0.0, 0.0, 1.0]]))
+    assert pts[1, 0] == pts[0, 0] and pts[1, 1] != pts[0, 1]  # meshgrid 'ij', x-major flatten
+    o, d, nears, fars = ns.orthographic_rays(pts, plane, batch=150, count=2)
+    assert o.shape[0] == 50 and torch.all(nears == 0) and torch.allclose(fars, torch.ones(50, 1))
+    starts, ends = ns.uniform_bins(nears, fars, 5)
+    assert torch.allclose(starts[0, :, 0], torch.tensor([0.0, 0.2, 0.4, 0.6, 0.8]))
+
+
+@pytest.mark.parametrize("name", ["small", "big"])
+def test_field_forward_golden(name):
+    g = np.load(GOLD / "field_forward.npz")
+    v = syn.SMALL if name == "small" else syn.BIG
+    sd = syn.field_state(geo=v["geo"], sem_dims=v["sem_dims"], log2_hashmap_size=v["log2_hashmap_size"], num_images=7,
+                         table_scale=0.5, weight_gain=1.5)
+    spec = fr.FieldSpec(max_res=v["max_res"], log2_hashmap_size=v["log2_hashmap_size"], geo_feat_dim=v["geo"])
+    o, d, s, e, cam = syn.ray_batch(32, 24, salt=77, far=3.0, num_images=7)
+    for mode, contraction in (("train", True), ("mean", False)):
+        f = fr.field_forward(sd, spec, o[:, None, :], d[:, None, :], s[..., None], e[..., None], cam, contraction=contraction, appearance=mode)
+        r = fr.render(f, s[..., None], e[..., None], training=True)
+        tag = f"{name}_{mode}"
+        for k in ("density", "rgb", "semantics"):
+            assert np.allclose(f[k].numpy(), g[f"{tag}_{k}"], rtol=1e-5, atol=1e-7), (tag, k)
+        for k in ("rgb", "accumulation", "semantics", "weights"):
+            assert np.allclose(r[k].numpy(), g[f"{tag}_render_{k}"], rtol=1e-5, atol=1e-7), (tag, k)
+        assert np.array_equal(r["depth_index"].numpy(), g[f"{tag}_render_depth_index"])
+
+
+def test_oracle_gradients_match_finite_differences():
+    """Central differences in float64 through the whole oracle path (field + compositing + losses),
+    including the semantic detach (fruit_field.py:264-265, fruit_nerf.py:343-345)."""
+    torch.manual_seed(0)
+    sd = syn.field_state(log2_hashmap_size=8, num_images=3, table_scale=0.5, weight_gain=1.5)
+    sd = {k: v.double() for k, v in sd.items()}
+    spec = fr.FieldSpec(log2_hashmap_size=8)
+    spec.scalings = lambda: ns.hash_scalings(16, 16, 2048).double()
+    o, d, s, e, cam = syn.ray_batch(3, 6, salt=2, far=2.0, num_images=3)
+    o, d, s, e = o.double(), d.double(), s.double(), e.double()
+    img, mask = syn.targets(3)
+
+    def loss_fn(state, with_sem=True):
+        f = fr.field_forward(state, spec, o[:, None, :], d[:, None, :], s[..., None], e[..., None], cam, True, "train")
+        r = fr.render(f, s[..., None], e[..., None], training=True)
+        ld = fr.loss_dict(r, img.double(), mask.double())
+        return ld["rgb_loss"] + (ld["semantics_loss"] if with_sem else 0.0)
+
+    # parameters upstream of the detach points are checked on the rgb loss only: finite differences
+    # see through detach(), autograd (by design of the reference) does not
+    for key, with_sem in (("mlp_head.layers.1.weight", True), ("mlp_base_mlp.layers.1.bias", False),
+                          ("mlp_semantics.layers.0.weight", True), ("mlp_base_grid.hash_table", False)):
+        st = {k: v.clone() for k, v in sd.items()}
+        st[key].requires_grad_(True)
+        loss_fn(st, with_sem).backward()
+        g = st[key].grad.reshape(-1)
+        flat = sd[key].reshape(-1)
+        nz = torch.nonzero(g).reshape(-1)
+        for i in (int(nz[0]), int(nz[len(nz) // 2]), int(nz[-1])):
+            def at(delta):
+                s2 = {k: v.clone() for k, v in sd.items()}
+                s2[key].reshape(-1)[i] += delta
+                return float(loss_fn(s2, with_sem))
+            fd = (at(1e-6) - at(-1e-6)) / 2e-6
+            assert abs(fd - float(g[i])) <= 1e-5 * max(1.0, abs(fd)) + 1e-8, (key, i, fd, float(g[i]))
+    # the semantic loss must not reach the base MLP (detach) -- compare with a semantics-only loss
+    st = {k: v.clone() for k, v in sd.items()}
+    st["mlp_base_mlp.layers.0.weight"].requires_grad_(True)
+    f = fr.field_forward(st, spec, o[:, None, :], d[:, None, :], s[..., None], e[..., None], cam, True, "train")
+    r = fr.render(f, s[..., None], e[..., None], training=True)
+    assert not r["semantics"].sum().requires_grad or torch.autograd.grad(r["semantics"].sum(), st["mlp_base_mlp.layers.0.weight"], allow_unused=True)[0] is None
