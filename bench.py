@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- rays/s of the FruitNeRF hot path (fused field + compositing, forward + backward) on
+synthetic 4096-ray x 192-sample batches (BASELINE.json metric), N GPUs of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--variant small|big] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch: render forward (hash encode -> MLPs ->
+composite), MSE + BCE loss, backward into the flat gradient buffer (and, for N > 1, one NCCL
+all-reduce of that buffer -- the reference's DDP exchange, fruit_pipeline.py:117).  Prints ONE JSON
+line on rank 0.  See DESIGN.md "Measurement" for the definitions of every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+R_RAYS, S_SAMPLES = 4096, 192
+NUM_IMAGES = 100
+HASH_BYTES_PER_POINT_FWD = 16 * 8 * 2 * 4  # L levels x 8 corners x F=2 x fp32
+HASH_BYTES_PER_POINT_BWD = 2 * HASH_BYTES_PER_POINT_FWD  # read-modify-write scatter
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        j = json.loads(p.read_text())
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) > 2 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) > 2 and r[2].isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def build_field(variant: str, device, table_scale: float = 1e-1):
+    """Random-init FruitField of the named variant, parameters from torch's RNG."""
+    from fruitnerf_b200.fruit_field import FruitField, SceneContraction
+
+    torch.manual_seed(0)
+    kw = dict(geo_feat_dim=15, max_res=2048, log2_hashmap_size=19, num_layers_semantic=2, hidden_dim_semantics=64)
+    if variant == "big":
+        kw = dict(geo_feat_dim=30, max_res=4096, log2_hashmap_size=21, num_layers_semantic=3, hidden_dim_semantics=128)
+    aabb = torch.tensor([[-1.0, -1, -1], [1, 1, 1]])
+    f = FruitField(aabb, num_images=NUM_IMAGES, use_semantics=True, num_semantic_classes=1,
+                   spatial_distortion=SceneContraction(order=float("inf")), **kw)
+    with torch.no_grad():
+        f.mlp_base_grid.hash_table.mul_(table_scale / 1e-3)  # U(-1,1) * table_scale
+    return f.to(device).train()
+
+
+def step_fn(field, batch, world, impl_id):
+    """One step through the public op (the call FruitModel.get_outputs makes)."""
+    from fruitnerf_b200 import ops
+
+    o, d, s, e, cam, img, mask = batch
+    out = ops.render(field.kernel_shape(), field.kernel_params(), o, d, s, e, cam, field.position_mode(), field.appearance_mode(),
+                     impl=impl_id)
+    loss = torch.nn.functional.mse_loss(img, out["rgb"]) + torch.nn.functional.binary_cross_entropy_with_logits(
+        out["semantics"][:, None], mask)
+    return out, loss
+
+
+def run_ours(args):
+    from fruitnerf_b200 import _lib as L
+    from fruitnerf_b200 import ops
+    from fruitnerf_b200 import synthetic as syn
+
+    L.load()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs CUDA devices (no CPU fallback in the product path)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    impl_id = {"auto": L.FNR_IMPL_AUTO, "simt": L.FNR_IMPL_SIMT, "tcgen05": L.FNR_IMPL_TCGEN05}[args.kernel]
+    field = build_field(args.variant, dev)
+    params = field.kernel_params()
+    N_pts = R_RAYS * S_SAMPLES
+
+    # per-rank batch (weak scaling: each rank draws its own 4096 rays, fruit_pipeline.py:97-99)
+    o, d, s, e, cam = syn.ray_batch(R_RAYS, S_SAMPLES, salt=rank, num_images=NUM_IMAGES)
+    img, mask = syn.targets(R_RAYS, salt=rank)
+    host = [t.pin_memory() for t in (o, d, s, e, cam.to(torch.int32), img, mask)]
+    batch = [t.to(dev) for t in host]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def one_step(b, timing=None):
+        for p in params:
+            p.grad = None
+        if timing:
+            timing[0].record()
+        out, loss = step_fn(field, b, world, impl_id)
+        if timing:
+            timing[1].record()
+        loss.backward()
+        flat = ops._Render.last_flat_grad
+        if timing:
+            timing[2].record()
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        if timing:
+            timing[3].record()
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        one_step(batch)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.fill_(float(i))  # evict the table / weights from L2 between timed steps
+        one_step(batch, evs[i])
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    step_ms = [ev[0].elapsed_time(ev[3]) for ev in evs]
+    fwd_ms = [ev[0].elapsed_time(ev[1]) for ev in evs]
+    bwd_ms = [ev[1].elapsed_time(ev[2]) for ev in evs]
+    total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms)
+
+    # end-to-end through the public op with HOST buffers: H2D of the step's rays/targets and a
+    # D2H read of the loss inside the timed region
+    e2e_steps = args.steps
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        b = [t.to(dev, non_blocking=True) for t in host]
+        loss = one_step(b)
+        _ = float(loss)  # D2H
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s)
+    h2d = sum(t.numel() * t.element_size() for t in host)
+
+    if rank != 0:
+        return
+    peak, peak_src = _peaks()
+    mean_fwd, mean_bwd = sum(fwd_ms) / len(fwd_ms), sum(bwd_ms) / len(bwd_ms)
+    dominant_is_bwd = mean_bwd >= mean_fwd
+    dom_ms = mean_bwd if dominant_is_bwd else mean_fwd
+    dom_bytes = N_pts * (HASH_BYTES_PER_POINT_BWD if dominant_is_bwd else HASH_BYTES_PER_POINT_FWD)
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    fwd_achieved = N_pts * HASH_BYTES_PER_POINT_FWD / (mean_fwd * 1e-3) / 1e9
+    line = {
+        "metric": "rays/sec (4096 rays x 192 samples) fused fwd+bwd",
+        "value": world * R_RAYS * args.steps / (total_ms * 1e-3),
+        "unit": "rays/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {
+            "workload": f"fruit_nerf{'_big' if args.variant == 'big' else ''} field ({args.variant}): {R_RAYS} rays x {S_SAMPLES} samples "
+                        "per GPU, render fwd + MSE/BCE loss + bwd" + (" + NCCL grad all-reduce" if world > 1 else ""),
+            "variant": args.variant,
+            "kernel": args.kernel,
+            "rays_per_gpu": R_RAYS,
+            "samples_per_ray": S_SAMPLES,
+            "l2": "flushed between timed steps (256 MiB fill); per-step CUDA-event durations summed",
+            "parallelism": f"dp{world}",
+        },
+        "fwd_ms": mean_fwd,
+        "bwd_ms": mean_bwd,
+        "fwd_rays_per_s": R_RAYS / (mean_fwd * 1e-3),
+        "roofline": {
+            "kernel": "render backward (simt_field_backward_kernel + composite bwd)" if dominant_is_bwd else "render forward",
+            "bound": "hbm",
+            "achieved": achieved,
+            "peak": peak,
+            "unit": "GB/s",
+            "frac": achieved / peak,
+            "traffic": None,
+            "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": dom_bytes,
+            "launch_ms": dom_ms,
+        },
+        "roofline_forward": {"bound": "hbm", "achieved": fwd_achieved, "peak": peak, "unit": "GB/s", "frac": fwd_achieved / peak,
+                             "launch_ms": mean_fwd, "algorithmic_bytes_per_launch": N_pts * HASH_BYTES_PER_POINT_FWD},
+        "e2e": {"value": world * R_RAYS * e2e_steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": 4 * args.steps,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(args.variant, sample_rays=args.cpu_rays, repeats=1)
+    print(json.dumps(line))
+
+
+def cpu_baseline(variant: str, sample_rays: int, repeats: int):
+    """The oracle (a port: pure-PyTorch restatement of the reference's CPU-runnable torch path) on
+    the host cores, fwd+bwd on a bounded sample of the same workload."""
+    from fruitnerf_b200 import synthetic as syn
+    from oracle import fruit_ref as fr
+
+    v = syn.SMALL if variant == "small" else syn.BIG
+    sd = syn.field_state(geo=v["geo"], sem_dims=v["sem_dims"], log2_hashmap_size=v["log2_hashmap_size"], num_images=NUM_IMAGES,
+                         table_scale=1e-1)
+    spec = fr.FieldSpec(max_res=v["max_res"], log2_hashmap_size=v["log2_hashmap_size"], geo_feat_dim=v["geo"])
+    o, d, s, e, cam = syn.ray_batch(sample_rays, S_SAMPLES, num_images=NUM_IMAGES)
+    img, mask = syn.targets(sample_rays)
+    best = None
+    for _ in range(repeats + 1):  # first pass = warm-up
+        st = {k: t.clone().requires_grad_(t.is_floating_point() and k != "aabb") for k, t in sd.items()}
+        t0 = time.perf_counter()
+        f = fr.field_forward(st, spec, o[:, None, :], d[:, None, :], s[..., None], e[..., None], cam, True, "train")
+        r = fr.render(f, s[..., None], e[..., None], training=True)
+        ld = fr.loss_dict(r, img, mask)
+        (ld["rgb_loss"] + ld["semantics_loss"]).backward()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": sample_rays / best, "unit": "rays/s", "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": "port",
+            "sample": f"{sample_rays} rays x {S_SAMPLES} samples of the same workload, fwd+bwd, best of {repeats} after 1 warm-up"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference's
+    arithmetic lives in nerfstudio/tinycudann (absent, not installable: BASELINE.md section 2), so
+    the arm is the oracle port on all host threads; each step = a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rays = args.cpu_rays
+    vals = []
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_baseline(args.variant, rays, repeats=0)
+    t_all = time.perf_counter()
+    for _ in range(max(1, min(args.steps, 3))):
+        vals.append(cpu_baseline(args.variant, rays, repeats=0))
+    dt = time.perf_counter() - t_all
+    v = sum(x["value"] for x in vals) / len(vals)
+    line = {
+        "impl": "reference",
+        "metric": "rays/sec (4096 rays x 192 samples) fused fwd+bwd",
+        "value": v,
+        "unit": "rays/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": len(vals),
+        "warmup": 1,
+        "ms_per_step": dt / len(vals) * 1e3,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"fruit_nerf field ({args.variant}): {rays}-ray x {S_SAMPLES}-sample sample of the 4096x192 batch, fwd+bwd, CPU",
+                   "variant": args.variant},
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{rays} rays x {S_SAMPLES} samples per step"},
+        "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--variant", default="small", choices=["small", "big"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--cpu-rays", type=int, default=2048)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
