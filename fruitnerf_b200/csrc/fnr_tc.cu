@@ -1,11 +1,612 @@
-// Fused tcgen05 render forward (placeholder until the kernel lands in this file).
+// Fused render forward for sm_100a: hash-grid gather -> base / semantic / colour MLPs on the 5th-gen
+// tensor cores (tcgen05.mma, accumulators in TMEM) -> per-ray alpha compositing, one persistent CTA
+// per SM.  (fruit_nerf/fruit_field.py:168-301 + fruit_nerf/fruit_nerf.py:320-348 in one pass.)
+//
+// Work decomposition
+//   * A CTA owns a group of G whole rays (G*S <= kMaxGroupPoints) at a time; its points are processed
+//     in rounds of kSlots*128 points.  A "slot" is 4 warps = 128 threads = the 128 rows (TMEM lanes)
+//     of an M=128 MMA tile; thread r of a slot owns point r of the tile from the gather to the heads.
+//     Slots only meet at the per-group compositing step, so one slot's gathers overlap the other
+//     slot's tensor-core round trips.
+//   * Gather: per level 8 float2 loads (read-only path), trilinear blend in registers, 32 features.
+//   * MLPs: every layer is D[128,N] (TMEM, fp32) = A[128,K] (smem, bf16) x W[N,K]^T (smem, bf16), with
+//     both operands split x = hi + lo (two bf16 each) and three MMAs per K-step
+//     (A_hi W_hi + A_lo W_hi + A_hi W_lo): ~2^-16 relative error per product, i.e. fp32-class parity
+//     (north_star 1e-3) at 3x the tensor work -- affordable because the path is gather-bound
+//     (DESIGN.md).  The epilogue thread reads its row with tcgen05.ld, adds the bias, applies ReLU,
+//     re-splits and stores the next layer's A row (canonical K-major layout, 16-byte vector stores).
+//     The last semantic layer (no activation) is folded into the 1-logit head at weight-staging time.
+//   * Compositing: per-sample density / rgb / logit stay in shared memory; one warp per ray scans.
+//
+// Shapes: the fruit_nerf family (geo 15, semantic 15-64-64, colour 63-64-64-3).  Everything else is
+// served by the simt kernels (tc_supported() == false).
 #include "fnr_common.cuh"
 #include "fnr_kernels.h"
+#include "fnr_tcgen05.cuh"
+
 namespace fnr {
-bool tc_supported(Family, const KField&, const KRays&) { return false; }
-int launch_tc_render_forward(Family, const KField&, const KParams&, const KRays&, const KFieldOut&, const KComposite&,
-                             cudaStream_t) {
-  set_error("tcgen05 render kernel not built");
-  return FNR_ERR_UNSUPPORTED;
+using namespace tc;
+
+namespace {
+
+constexpr int kSlots = 2;
+constexpr int kCtaThreads = kSlots * 128;
+constexpr int kMaxGroupPoints = 768;
+constexpr int kTmemColsPerSlot = 160;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// ---- small-family dimensions -------------------------------------------------------------------
+constexpr int GEO = 15, ENC = 32, H = 64, APP = 32, SHD = 16;
+// padded GEMM shapes (K multiple of 16, N multiple of 16)
+constexpr int K_BASE0 = 32, N_BASE0 = 64;
+constexpr int K_BASE1 = 64, N_BASE1 = 16;
+constexpr int K_SEM0 = 16, N_SEM0 = 64;
+constexpr int K_SEMH = 64, N_SEMH = 16;   // folded (semantic layer 1) x head
+constexpr int K_COL0 = 64, N_COL0 = 64;   // K order: [sh 16 | app 32 | geo 15 | 0]
+constexpr int K_COL1 = 64, N_COL1 = 64;
+constexpr int K_COL2 = 64, N_COL2 = 16;
+
+// shared-memory map (bytes).  Weight tiles: hi then lo, canonical layout with ROWS = N.
+constexpr int wbytes(int n, int k) { return n * k * 2; }
+constexpr int OFF_W_BASE0 = 0;
+constexpr int OFF_W_BASE1 = OFF_W_BASE0 + 2 * wbytes(N_BASE0, K_BASE0);
+constexpr int OFF_W_SEM0 = OFF_W_BASE1 + 2 * wbytes(N_BASE1, K_BASE1);
+constexpr int OFF_W_SEMH = OFF_W_SEM0 + 2 * wbytes(N_SEM0, K_SEM0);
+constexpr int OFF_W_COL0 = OFF_W_SEMH + 2 * wbytes(N_SEMH, K_SEMH);
+constexpr int OFF_W_COL1 = OFF_W_COL0 + 2 * wbytes(N_COL0, K_COL0);
+constexpr int OFF_W_COL2 = OFF_W_COL1 + 2 * wbytes(N_COL1, K_COL1);
+constexpr int OFF_BIAS = OFF_W_COL2 + 2 * wbytes(N_COL2, K_COL2);
+// biases (floats): base0[64] base1[16] sem0[64] semh[16] col0[64] col1[64] col2[16] app[32]
+constexpr int B_BASE0 = 0, B_BASE1 = 64, B_SEM0 = 80, B_SEMH = 144, B_COL0 = 160, B_COL1 = 224, B_COL2 = 288, B_APP = 304,
+              B_COUNT = 336;
+constexpr int OFF_TILES = OFF_BIAS + B_COUNT * 4;
+// per-slot activation tiles: P (K=64 hi+lo), Q (K=64 hi+lo; the K=32 encoding tile aliases it), S (K=16 hi+lo)
+constexpr int TILE_P = 0, TILE_Q = 2 * 128 * 64 * 2, TILE_S = 2 * TILE_Q, SLOT_TILE_BYTES = TILE_S + 2 * 128 * 16 * 2;
+constexpr int OFF_SAMPLES = OFF_TILES + kSlots * SLOT_TILE_BYTES;  // [kMaxGroupPoints][5] floats
+constexpr int OFF_END = OFF_SAMPLES + kMaxGroupPoints * 5 * 4;
+constexpr int kSmemBytes = OFF_END + 1024;  // + alignment slack
+static_assert(kSmemBytes <= 227 * 1024, "shared-memory budget");
+static_assert(OFF_TILES % 16 == 0 && SLOT_TILE_BYTES % 16 == 0 && OFF_BIAS % 16 == 0, "alignment");
+
+// TMEM column map inside a slot's kTmemColsPerSlot window
+constexpr int C_R0 = 0;    // 64 cols: base0 out, later colour0 out, colour1 out
+constexpr int C_R1 = 64;   // 16 cols: base1 out, later semantic-head out, colour2 out
+constexpr int C_R2 = 80;   // 64 cols: semantic0 out
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+
+// Stage W[N][K] (fp32, torch layout, optional column permutation / row padding) into the canonical
+// bf16 hi/lo tiles.  getw(n, k) returns the fp32 weight of padded position (n, k).
+template <int NP, int KP, class F>
+__device__ __forceinline__ void stage_weight(uint8_t* tile, F getw) {
+  for (int idx = threadIdx.x; idx < NP * KP; idx += kCtaThreads) {
+    const int n = idx / KP, k = idx % KP;
+    float hi, lo;
+    split_bf16(getw(n, k), hi, lo);
+    const int off = (k >> 3) * (NP * 16) + n * 16 + (k & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(tile + off) = __float2bfloat16_rn(hi);
+    *reinterpret_cast<__nv_bfloat16*>(tile + wbytes(NP, KP) + off) = __float2bfloat16_rn(lo);
+  }
+}
+
+// Store 8 consecutive K elements of this thread's row (chunk j) as hi/lo bf16.
+__device__ __forceinline__ void store_chunk(uint8_t* tile_hi, int lo_off, int row, int j, const float (&v)[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float h0, l0, h1, l1;
+    split_bf16(v[2 * q], h0, l0);
+    split_bf16(v[2 * q + 1], h1, l1);
+    h[q] = pack_bf16x2(h0, h1);
+    l[q] = pack_bf16x2(l0, l1);
+  }
+  uint8_t* p = tile_hi + j * (128 * 16) + row * 16;
+  *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(p + lo_off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// Issue the 3-way split GEMM D[128,N] = A[128,K] W[N,K]^T (one thread).
+template <int K, int N>
+__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_hi, uint32_t w_hi) {
+  constexpr uint32_t idesc = idesc_bf16_f32(128, N);
+  constexpr uint32_t a_lo_off = 128 * K * 2, w_lo_off = N * K * 2;
+#pragma unroll
+  for (int ks = 0; ks < K / 16; ++ks) {
+    const uint64_t ah = smem_desc(a_hi + ks * 2 * 128 * 16, 128 * 16, 128);
+    const uint64_t al = smem_desc(a_hi + a_lo_off + ks * 2 * 128 * 16, 128 * 16, 128);
+    const uint64_t wh = smem_desc(w_hi + ks * 2 * N * 16, N * 16, 128);
+    const uint64_t wl = smem_desc(w_hi + w_lo_off + ks * 2 * N * 16, N * 16, 128);
+    mma_ss(d_tmem, ah, wh, idesc, ks > 0);
+    mma_ss(d_tmem, al, wh, idesc, true);
+    mma_ss(d_tmem, ah, wl, idesc, true);
+  }
+}
+
+__device__ __forceinline__ float warp_incl_scan_f(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_up_sync(kFullMask, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  return v;
+}
+
+struct TcArgs {
+  KField F;
+  KParams P;
+  KRays Rr;
+  KFieldOut O;
+  KComposite Cm;
+  int rays_per_group;
+  int composite;
+};
+
+__global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const __grid_constant__ TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t s_bar[kSlots];
+  __shared__ uint32_t s_tmem_base;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slot = warp >> 2;
+  const int row = (warp & 3) * 32 + lane;  // TMEM lane of this thread (warp w may touch lanes 32*(w%4)..)
+  const KParams& P = a.P;
+  const KField& F = a.F;
+  float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
+  float* s_samples = reinterpret_cast<float*>(smem + OFF_SAMPLES);
+
+  // ---- one-time setup: TMEM, barriers, weights ------------------------------------------------
+  if (warp == 0) tmem_alloc(&s_tmem_base, 512);
+  if (tid == 0) {
+    for (int i = 0; i < kSlots; ++i) mbar_init(&s_bar[i], 1);
+    mbar_fence_init();
+  }
+  stage_weight<N_BASE0, K_BASE0>(smem + OFF_W_BASE0, [&](int n, int k) { return __ldg(P.base_w[0] + n * ENC + k); });
+  stage_weight<N_BASE1, K_BASE1>(smem + OFF_W_BASE1, [&](int n, int k) { return __ldg(P.base_w[1] + n * H + k); });
+  stage_weight<N_SEM0, K_SEM0>(smem + OFF_W_SEM0, [&](int n, int k) { return k < GEO ? __ldg(P.sem_w[0] + n * GEO + k) : 0.f; });
+  // fold: logit = head_w . (W1 z + b1) + head_b  =>  row 0 of the N=16 tile is head_w^T W1
+  stage_weight<N_SEMH, K_SEMH>(smem + OFF_W_SEMH, [&](int n, int k) {
+    if (n != 0) return 0.f;
+    float acc = 0.f;
+    for (int j = 0; j < H; ++j) acc = fmaf(__ldg(P.head_w + j), __ldg(P.sem_w[1] + j * H + k), acc);
+    return acc;
+  });
+  // colour layer 0 with the K order [sh | app | geo | 0] (torch order is [sh | geo | app])
+  stage_weight<N_COL0, K_COL0>(smem + OFF_W_COL0, [&](int n, int k) {
+    const float* w = P.col_w[0] + n * (SHD + GEO + APP);
+    if (k < SHD) return __ldg(w + k);
+    if (k < SHD + APP) return __ldg(w + SHD + GEO + (k - SHD));
+    if (k < SHD + APP + GEO) return __ldg(w + SHD + (k - SHD - APP));
+    return 0.f;
+  });
+  stage_weight<N_COL1, K_COL1>(smem + OFF_W_COL1, [&](int n, int k) { return __ldg(P.col_w[1] + n * H + k); });
+  stage_weight<N_COL2, K_COL2>(smem + OFF_W_COL2, [&](int n, int k) { return n < 3 ? __ldg(P.col_w[2] + n * H + k) : 0.f; });
+  for (int i = tid; i < B_COUNT; i += kCtaThreads) {
+    float v = 0.f;
+    if (i < B_BASE1) v = __ldg(P.base_b[0] + i);
+    else if (i < B_SEM0) v = __ldg(P.base_b[1] + (i - B_BASE1));
+    else if (i < B_SEMH) v = __ldg(P.sem_b[0] + (i - B_SEM0));
+    else if (i == B_SEMH) {
+      float acc = __ldg(P.head_b);
+      for (int j = 0; j < H; ++j) acc = fmaf(__ldg(P.head_w + j), __ldg(P.sem_b[1] + j), acc);
+      v = acc;
+    } else if (i < B_COL0) v = 0.f;
+    else if (i < B_COL1) v = __ldg(P.col_b[0] + (i - B_COL0));
+    else if (i < B_COL2) v = __ldg(P.col_b[1] + (i - B_COL1));
+    else if (i < B_COL2 + 3) v = __ldg(P.col_b[2] + (i - B_COL2));
+    else if (i >= B_APP && F.appearance_mode == FNR_APP_MEAN) {
+      float acc = 0.f;
+      for (int r = 0; r < F.num_images; ++r) acc += __ldg(P.app_embedding + (size_t)r * APP + (i - B_APP));
+      v = acc / (float)F.num_images;
+    }
+    s_bias[i] = v;
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+
+  const uint32_t tmem_slot = s_tmem_base + slot * kTmemColsPerSlot;
+  const uint32_t tmem_row = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16);
+  uint8_t* tiles = smem + OFF_TILES + slot * SLOT_TILE_BYTES;
+  uint8_t* tP = tiles + TILE_P;
+  uint8_t* tQ = tiles + TILE_Q;
+  uint8_t* tS = tiles + TILE_S;
+  const uint32_t aP = smem_u32(tP), aQ = smem_u32(tQ), aS = smem_u32(tS);
+  const uint32_t wBase = smem_u32(smem);
+  uint64_t* bar = &s_bar[slot];
+  uint32_t phase = 0;
+  const bool issuer = (warp & 3) == 0 && lane == 0;
+  const int bar_id = 1 + slot;
+
+  const int S = a.Rr.S, R = a.Rr.R;
+  const int G = a.rays_per_group;
+  const int num_groups = (R + G - 1) / G;
+  const float2* __restrict__ table = reinterpret_cast<const float2*>(P.hash_table);
+  const uint32_t hmask = (1u << F.log2T) - 1u;
+
+  for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
+    const int ray0 = group * G;
+    const int rays_here = min(G, R - ray0);
+    const int pts = rays_here * S;
+    const int rounds = (pts + kCtaThreads - 1) / kCtaThreads;
+
+    for (int rd = 0; rd < rounds; ++rd) {
+      const int local = rd * kCtaThreads + slot * 128 + row;  // point index inside the group
+      const bool valid = local < pts;
+      const int lc = valid ? local : pts - 1;
+      const int ray = ray0 + lc / S;
+      const size_t gp = (size_t)ray0 * S + lc;  // global point index
+      const float* o = a.Rr.origins + 3 * (size_t)ray;
+      const float* d = a.Rr.directions + 3 * (size_t)ray;
+      bool sel;
+      const Vec3 pos = field_position(o, d, __ldg(a.Rr.starts + gp), __ldg(a.Rr.ends + gp), F.position_mode, F.aabb, sel);
+
+      // ---- gather + trilinear blend -> encoding tile (aliases Q) -----------------------------
+      {
+        float enc[ENC];
+#pragma unroll
+        for (int l = 0; l < 16; ++l) {
+          const LevelCell c = level_cell(pos, F.scalings[l]);
+          const uint32_t base = (uint32_t)l << F.log2T;
+          float2 f[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = __ldg(table + corner_row(c, k, hmask, base));
+          const float2 r = trilerp(f, c);
+          enc[2 * l] = r.x;
+          enc[2 * l + 1] = r.y;
+        }
+        if (a.O.stash_encoding && valid) {
+          float4* st = reinterpret_cast<float4*>(a.O.stash_encoding + gp * ENC);
+#pragma unroll
+          for (int i = 0; i < ENC / 4; ++i) st[i] = make_float4(enc[4 * i], enc[4 * i + 1], enc[4 * i + 2], enc[4 * i + 3]);
+        }
+#pragma unroll
+        for (int j = 0; j < K_BASE0 / 8; ++j) {
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = enc[8 * j + q];
+          store_chunk(tQ, 128 * K_BASE0 * 2, row, j, v);
+        }
+      }
+      fence_async_smem();
+      fence_before_sync();
+      named_bar_sync(bar_id, 128);
+      if (issuer) {
+        fence_after_sync();
+        issue_gemm<K_BASE0, N_BASE0>(tmem_slot + C_R0, aQ, wBase + OFF_W_BASE0);
+        mma_commit(bar);
+      }
+
+      // ---- epilogue 1: h1 = relu(base0 + b) -> P ; sh / appearance part of the colour input -> Q later
+      float sh[SHD], app[APP];
+      sh_degree4(__ldg(d), __ldg(d + 1), __ldg(d + 2), sh);
+      if (F.appearance_mode == FNR_APP_PER_CAMERA) {
+        const float4* e4 = reinterpret_cast<const float4*>(P.app_embedding + (size_t)__ldg(a.Rr.camera_indices + ray) * APP);
+#pragma unroll
+        for (int i = 0; i < APP / 4; ++i) {
+          const float4 v = __ldg(e4 + i);
+          app[4 * i] = v.x;
+          app[4 * i + 1] = v.y;
+          app[4 * i + 2] = v.z;
+          app[4 * i + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < APP; ++i) app[i] = s_bias[B_APP + i];
+      }
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      fence_after_sync();
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tmem_row + C_R0, r0);
+        tmem_ld32(tmem_row + C_R0 + 32, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int n = 8 * j + q;
+            const float x = __uint_as_float(n < 32 ? r0[n] : r1[n - 32]) + s_bias[B_BASE0 + n];
+            v[q] = fmaxf(x, 0.f);
+          }
+          store_chunk(tP, 128 * 64 * 2, row, j, v);
+        }
+      }
+      fence_async_smem();
+      fence_before_sync();
+      named_bar_sync(bar_id, 128);
+      if (issuer) {
+        fence_after_sync();
+        issue_gemm<K_BASE1, N_BASE1>(tmem_slot + C_R1, aP, wBase + OFF_W_BASE1);
+        mma_commit(bar);
+      }
+      // colour-input chunks that do not depend on geo: [sh 0..15 | app 0..31] = chunks 0..5 of Q
+      // (the encoding tile in Q is dead: its GEMM completed before epilogue 1 ran)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = sh[8 * j + q];
+        store_chunk(tQ, 128 * 64 * 2, row, j, v);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = app[8 * j + q];
+        store_chunk(tQ, 128 * 64 * 2, row, 2 + j, v);
+      }
+
+      // ---- epilogue 2: [h0 | geo] ; density ; geo -> S (semantic input) and chunks 6,7 of Q --------
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      fence_after_sync();
+      float density;
+      {
+        uint32_t r0[16];
+        tmem_ld16(tmem_row + C_R1, r0);
+        tmem_ld_wait();
+        float outv[16];
+#pragma unroll
+        for (int n = 0; n < 16; ++n) outv[n] = __uint_as_float(r0[n]) + s_bias[B_BASE1 + n];
+        density = sel ? expf(outv[0]) : 0.f;
+        float g0[8], g1[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          g0[q] = outv[1 + q];
+          g1[q] = q < 7 ? outv[9 + q] : 0.f;
+        }
+        store_chunk(tS, 128 * 16 * 2, row, 0, g0);
+        store_chunk(tS, 128 * 16 * 2, row, 1, g1);
+        store_chunk(tQ, 128 * 64 * 2, row, 6, g0);
+        store_chunk(tQ, 128 * 64 * 2, row, 7, g1);
+      }
+      fence_async_smem();
+      fence_before_sync();
+      named_bar_sync(bar_id, 128);
+      if (issuer) {
+        fence_after_sync();
+        issue_gemm<K_SEM0, N_SEM0>(tmem_slot + C_R2, aS, wBase + OFF_W_SEM0);
+        issue_gemm<K_COL0, N_COL0>(tmem_slot + C_R0, aQ, wBase + OFF_W_COL0);
+        mma_commit(bar);
+      }
+
+      // ---- epilogue 3: z1 = relu(sem0 + b) -> P ; c1 = relu(col0 + b) -> Q -------------------------
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      fence_after_sync();
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        uint32_t r0[32], r1[32];
+        const uint32_t col = which == 0 ? C_R2 : C_R0;
+        tmem_ld32(tmem_row + col, r0);
+        tmem_ld32(tmem_row + col + 32, r1);
+        tmem_ld_wait();
+        const int boff = which == 0 ? B_SEM0 : B_COL0;
+        uint8_t* dst = which == 0 ? tP : tQ;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int n = 8 * j + q;
+            v[q] = fmaxf(__uint_as_float(n < 32 ? r0[n] : r1[n - 32]) + s_bias[boff + n], 0.f);
+          }
+          store_chunk(dst, 128 * 64 * 2, row, j, v);
+        }
+      }
+      fence_async_smem();
+      fence_before_sync();
+      named_bar_sync(bar_id, 128);
+      if (issuer) {
+        fence_after_sync();
+        issue_gemm<K_SEMH, N_SEMH>(tmem_slot + C_R1, aP, wBase + OFF_W_SEMH);
+        issue_gemm<K_COL1, N_COL1>(tmem_slot + C_R0, aQ, wBase + OFF_W_COL1);
+        mma_commit(bar);
+      }
+
+      // ---- epilogue 4: logit ; c2 = relu(col1 + b) -> P --------------------------------------------
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      fence_after_sync();
+      float logit;
+      {
+        uint32_t lg[8];
+        tmem_ld8(tmem_row + C_R1, lg);
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tmem_row + C_R0, r0);
+        tmem_ld32(tmem_row + C_R0 + 32, r1);
+        tmem_ld_wait();
+        logit = __uint_as_float(lg[0]) + s_bias[B_SEMH];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int n = 8 * j + q;
+            v[q] = fmaxf(__uint_as_float(n < 32 ? r0[n] : r1[n - 32]) + s_bias[B_COL1 + n], 0.f);
+          }
+          store_chunk(tP, 128 * 64 * 2, row, j, v);
+        }
+      }
+      fence_async_smem();
+      fence_before_sync();
+      named_bar_sync(bar_id, 128);
+      if (issuer) {
+        fence_after_sync();
+        issue_gemm<K_COL2, N_COL2>(tmem_slot + C_R1, aP, wBase + OFF_W_COL2);
+        mma_commit(bar);
+      }
+
+      // ---- epilogue 5: rgb = sigmoid(col2 + b) ; per-sample results to shared memory ---------------
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      fence_after_sync();
+      {
+        uint32_t c[8];
+        tmem_ld8(tmem_row + C_R1, c);
+        tmem_ld_wait();
+        if (valid) {
+          float* q = s_samples + 5 * local;
+          q[0] = density;
+          q[1] = sigmoidf_(__uint_as_float(c[0]) + s_bias[B_COL2]);
+          q[2] = sigmoidf_(__uint_as_float(c[1]) + s_bias[B_COL2 + 1]);
+          q[3] = sigmoidf_(__uint_as_float(c[2]) + s_bias[B_COL2 + 2]);
+          q[4] = logit;
+        }
+      }
+      fence_before_sync();  // order this round's TMEM reads before the next round's MMAs
+    }
+
+    // ---- per-group: write per-sample outputs, composite one ray per warp -------------------------
+    __syncthreads();
+    {
+      const size_t gbase = (size_t)ray0 * S;
+      for (int i = tid; i < pts; i += kCtaThreads) {
+        const float* q = s_samples + 5 * i;
+        if (a.O.sample_density) a.O.sample_density[gbase + i] = q[0];
+        if (a.O.sample_semantics) a.O.sample_semantics[gbase + i] = q[4];
+        if (a.O.sample_rgb) {
+          a.O.sample_rgb[3 * (gbase + i)] = q[1];
+          a.O.sample_rgb[3 * (gbase + i) + 1] = q[2];
+          a.O.sample_rgb[3 * (gbase + i) + 2] = q[3];
+        }
+      }
+    }
+    if (a.composite) {
+      const KComposite& Cm = a.Cm;
+      for (int rl = warp; rl < rays_here; rl += kCtaThreads / 32) {
+        const int r = ray0 + rl;
+        const size_t base = (size_t)r * S;
+        const float* sp = s_samples + 5 * (rl * S);
+        float run_x = 0.f, run_w = 0.f, acc = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, sem = 0.f;
+        int median = S;
+        for (int c0 = 0; c0 < S; c0 += 32) {
+          const int i = c0 + lane;
+          const bool in = i < S;
+          float x = 0.f, w = 0.f;
+          if (in) x = (a.Rr.ends[base + i] - a.Rr.starts[base + i]) * sp[5 * i];
+          const float incl = warp_incl_scan_f(x, lane);
+          if (in) {
+            const float alpha = 1.0f - expf(-x);
+            const float T = expf(-(run_x + (incl - x)));
+            w = nan_to_num(alpha * T);
+            if (Cm.weights) Cm.weights[base + i] = w;
+            float c0r = sp[5 * i + 1], c0g = sp[5 * i + 2], c0b = sp[5 * i + 3];
+            if (Cm.clamp_rgb) {
+              c0r = nan_to_num(c0r);
+              c0g = nan_to_num(c0g);
+              c0b = nan_to_num(c0b);
+            }
+            cr += w * c0r;
+            cg += w * c0g;
+            cb += w * c0b;
+            sem += w * sp[5 * i + 4];
+            acc += w;
+          }
+          const float wincl = warp_incl_scan_f(w, lane);
+          const unsigned m = __ballot_sync(kFullMask, in && (run_w + wincl >= 0.5f));
+          if (m && median == S) median = c0 + (__ffs(m) - 1);
+          run_x += __shfl_sync(kFullMask, incl, 31);
+          run_w += __shfl_sync(kFullMask, wincl, 31);
+        }
+        acc = warp_sum_f(acc);
+        cr = warp_sum_f(cr);
+        cg = warp_sum_f(cg);
+        cb = warp_sum_f(cb);
+        sem = warp_sum_f(sem);
+        if (lane == 0) {
+          float lr = sp[5 * (S - 1) + 1], lg = sp[5 * (S - 1) + 2], lb = sp[5 * (S - 1) + 3];
+          if (Cm.clamp_rgb) {
+            lr = nan_to_num(lr);
+            lg = nan_to_num(lg);
+            lb = nan_to_num(lb);
+          }
+          float orr = cr + lr * (1.0f - acc), og = cg + lg * (1.0f - acc), ob = cb + lb * (1.0f - acc);
+          if (Cm.clamp_rgb) {
+            orr = fminf(fmaxf(orr, 0.f), 1.f);
+            og = fminf(fmaxf(og, 0.f), 1.f);
+            ob = fminf(fmaxf(ob, 0.f), 1.f);
+          }
+          if (Cm.rgb) {
+            Cm.rgb[3 * r] = orr;
+            Cm.rgb[3 * r + 1] = og;
+            Cm.rgb[3 * r + 2] = ob;
+          }
+          if (Cm.accumulation) Cm.accumulation[r] = acc;
+          if (Cm.semantics) Cm.semantics[r] = sem;
+          const int mi = median < S - 1 ? median : S - 1;
+          if (Cm.depth_index) Cm.depth_index[r] = mi;
+          if (Cm.depth) Cm.depth[r] = (a.Rr.starts[base + mi] + a.Rr.ends[base + mi]) / 2;
+        }
+      }
+    }
+    __syncthreads();  // s_samples is rewritten by the next group
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(s_tmem_base, 512);
+}
+
+int pick_rays_per_group(int S) {
+  if (S > kMaxGroupPoints) return 0;
+  int best = 0;
+  double best_waste = 2.0;
+  for (int g = 1; g * S <= kMaxGroupPoints; ++g) {
+    const int pts = g * S;
+    const int rounds = (pts + kCtaThreads - 1) / kCtaThreads;
+    const double waste = 1.0 - (double)pts / (rounds * kCtaThreads);
+    if (waste < best_waste - 1e-9 || (waste < best_waste + 1e-9 && g > best)) {
+      best_waste = waste;
+      best = g;
+    }
+  }
+  return best;
+}
+
+}  // namespace
+
+bool tc_supported(Family fam, const KField& F, const KRays& Rr) {
+  (void)F;
+  return fam == kFamilySmall && Rr.S >= 1 && Rr.S <= kMaxGroupPoints;
+}
+
+int launch_tc_render_forward(Family fam, const KField& F, const KParams& P, const KRays& Rr, const KFieldOut& O,
+                             const KComposite& Cm, cudaStream_t st) {
+  if (!tc_supported(fam, F, Rr)) {
+    set_error("tcgen05 render kernel does not support this shape");
+    return FNR_ERR_UNSUPPORTED;
+  }
+  if (Rr.R == 0) return FNR_OK;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_render_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tc_render_forward_kernel)");
+    configured = true;
+  }
+  TcArgs a;
+  a.F = F;
+  a.P = P;
+  a.Rr = Rr;
+  a.O = O;
+  a.Cm = Cm;
+  a.rays_per_group = pick_rays_per_group(Rr.S);
+  a.composite = Cm.rgb || Cm.accumulation || Cm.depth || Cm.depth_index || Cm.semantics || Cm.weights;
+  const int groups = (Rr.R + a.rays_per_group - 1) / a.rays_per_group;
+  const int grid = groups < sm_count() ? groups : sm_count();
+  tc_render_forward_kernel<<<grid, kCtaThreads, kSmemBytes, st>>>(a);
+  return check_cuda(cudaGetLastError(), "tc_render_forward_kernel");
+}
+
 }  // namespace fnr

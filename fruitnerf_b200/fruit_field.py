@@ -193,6 +193,16 @@ class FruitField(nn.Module):
 
     # -- native plumbing ---------------------------------------------------------------------
     def kernel_shape(self) -> ops.FieldShape:
+        """Static kernel description; cached (building it reads the aabb buffer, a device sync)."""
+        key = (self.pass_semantic_gradients, self.num_images, self.aabb._version, self.aabb.data_ptr())
+        cached = getattr(self, "_kernel_shape_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        shape = self._build_kernel_shape()
+        object.__setattr__(self, "_kernel_shape_cache", (key, shape))
+        return shape
+
+    def _build_kernel_shape(self) -> ops.FieldShape:
         g = self.mlp_base_grid
         return ops.FieldShape(
             num_levels=g.num_levels,

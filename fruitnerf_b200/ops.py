@@ -33,6 +33,13 @@ class FieldShape:
     pass_semantic_gradients: bool = False
 
     def desc(self, position_mode: int, appearance_mode: int, impl: int = L.FNR_IMPL_AUTO) -> L.FieldDesc:
+        cache = self.__dict__.setdefault("_desc_cache", {})
+        key = (position_mode, appearance_mode, impl)
+        if key not in cache:
+            cache[key] = self._make_desc(position_mode, appearance_mode, impl)
+        return cache[key]
+
+    def _make_desc(self, position_mode: int, appearance_mode: int, impl: int) -> L.FieldDesc:
         d = L.FieldDesc()
         d.num_levels = self.num_levels
         d.features_per_level = self.features_per_level
@@ -127,11 +134,15 @@ class _Render(torch.autograd.Function):
     def forward(ctx, shape: FieldShape, mode: Dict, origins, directions, starts, ends, camera_indices, *params):
         dev = _require_cuda(origins, directions, starts, ends, *params)
         lib = L.load()
+        ctx.set_materialize_grads(False)
         R, S = starts.shape[0], starts.shape[1]
         origins, directions, starts, ends = map(_f32c, (origins, directions, starts, ends))
         cam = None
         if camera_indices is not None:
-            cam = camera_indices.reshape(-1).to(torch.int32).contiguous()
+            cam = camera_indices.reshape(-1)
+            if cam.dtype != torch.int32:
+                cam = cam.to(torch.int32)
+            cam = cam.contiguous()
         params = [p.detach() for p in params]
         need_grad = any(ctx.needs_input_grad[7:])
         composite = mode["composite"]
