@@ -1,0 +1,105 @@
+"""FruitPipeline -- drop-in surface of fruit_nerf.fruit_pipeline.FruitPipeline (66-260).
+
+Differences that matter on B200: instead of wrapping the model in DDP (fruit_pipeline.py:117, NCCL
+all-reduce of every parameter's .grad in 25 MiB buckets) the backward kernels accumulate into ONE
+flat fp32 gradient buffer (ops.flat_zero_grads) and ``sync_gradients`` all-reduces that buffer in a
+single NCCL collective over NVLink/NVSwitch (mean over ranks, the DDP semantics).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Literal, Optional, Type
+
+import torch
+import torch.distributed as dist
+from torch import nn
+from torch.nn import Parameter
+
+from . import ops
+from .compat import InstantiateConfig
+from .data.fruit_datamanager import FruitDataManagerConfig
+from .fruit_nerf import FruitNerfModelConfig
+
+
+@dataclass
+class FruitPipelineConfig(InstantiateConfig):
+    """fruit_pipeline.py:54-63."""
+
+    _target: Type = field(default_factory=lambda: FruitPipeline)
+    datamanager: Any = field(default_factory=FruitDataManagerConfig)
+    model: Any = field(default_factory=FruitNerfModelConfig)
+
+
+def sync_gradients(flat_grad: torch.Tensor, world_size: int, group=None, async_op: bool = False):
+    """Mean all-reduce of the flat gradient buffer (the reference's DDP exchange)."""
+    if world_size <= 1:
+        return None
+    return dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG if flat_grad.is_cuda else dist.ReduceOp.SUM, group=group,
+                           async_op=async_op) if flat_grad.is_cuda else _cpu_mean_all_reduce(flat_grad, world_size, group)
+
+
+def _cpu_mean_all_reduce(t: torch.Tensor, world_size: int, group=None):
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)  # gloo has no AVG
+    t.div_(world_size)
+    return None
+
+
+class FruitPipeline(nn.Module):
+    """fruit_pipeline.py:66-260 (constructor signature and method names kept)."""
+
+    def __init__(self, config: FruitPipelineConfig, device: str, test_mode: Literal["test", "val", "inference", "export"] = "val",
+                 world_size: int = 1, local_rank: int = 0, grad_scaler: Optional[Any] = None):
+        super().__init__()
+        self.config = config
+        self.test_mode = test_mode
+        self.datamanager = config.datamanager.setup(device=device, test_mode=test_mode, world_size=world_size, local_rank=local_rank)
+        self.datamanager.to(device)
+        assert self.datamanager.train_dataset is not None, "Missing input dataset"  # fruit_pipeline.py:102
+        self._model = config.model.setup(
+            scene_box=self.datamanager.train_dataset.scene_box,
+            num_train_data=len(self.datamanager.train_dataset),
+            metadata=self.datamanager.train_dataset.metadata,
+            device=device,
+            grad_scaler=grad_scaler,
+            test_mode=test_mode,
+            render_rgb_inference=True,
+        )
+        self._model.to(device)
+        self.world_size = world_size
+        if world_size > 1:
+            dist.barrier()  # fruit_pipeline.py:118
+
+    @property
+    def model(self):
+        return self._model
+
+    @property
+    def device(self):
+        return self._model.device
+
+    def get_train_loss_dict(self, step: int):
+        """fruit_pipeline.py:120-146."""
+        ray_bundle, batch = self.datamanager.next_train(step)
+        model_outputs = self._model(ray_bundle)
+        metrics_dict = self.model.get_metrics_dict(model_outputs, batch)
+        loss_dict = self.model.get_loss_dict(model_outputs, batch, metrics_dict)
+        return model_outputs, loss_dict, metrics_dict
+
+    def sync_gradients(self):
+        """Call after ``loss.backward()``: one collective over the flat gradient buffer."""
+        flat = ops._Render.last_flat_grad
+        if flat is not None:
+            sync_gradients(flat, self.world_size)
+
+    def load_pipeline(self, loaded_state: Dict[str, Any], step: int) -> None:
+        """fruit_pipeline.py:229-240: strip DDP's ``module.`` prefix, strict load."""
+        state = {(key[len("module."):] if key.startswith("module.") else key): value for key, value in loaded_state.items()}
+        self.model.update_to_step(step)
+        self.load_state_dict(state, strict=True)
+
+    def get_training_callbacks(self, training_callback_attributes) -> List:
+        return self.datamanager.get_training_callbacks(training_callback_attributes)
+
+    def get_param_groups(self) -> Dict[str, List[Parameter]]:
+        """fruit_pipeline.py:251-260."""
+        return {**self.datamanager.get_param_groups(), **self.model.get_param_groups()}

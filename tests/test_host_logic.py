@@ -1,0 +1,176 @@
+"""CPU tests of the host-side mirror of the reference's plugin surface."""
+import os
+import socket
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from fruitnerf_b200 import synthetic as syn
+from fruitnerf_b200.compat import RayBundle, SceneBox, Semantics
+from fruitnerf_b200.components.ray_samplers import UniformLinDispPiecewiseSampler, UniformSamplerWithNoise
+from fruitnerf_b200.data.fruit_datamanager import FruitDataManager, FruitDataManagerConfig, get_corners_of_aabb, sample_surface_points
+from fruitnerf_b200.export.exporter_utils import write_ply
+from fruitnerf_b200.fruit_field import FruitField, SceneContraction
+from fruitnerf_b200.fruit_nerf import FruitModel, FruitNerfModel, FruitNerfModelConfig
+from fruitnerf_b200.fruit_nerf_config import METHODS
+from oracle import ns_torch as ns
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _field(**kw):
+    return FruitField(torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), num_images=5, use_semantics=True, num_semantic_classes=1,
+                      log2_hashmap_size=10, spatial_distortion=SceneContraction(), **kw)
+
+
+def test_state_dict_keys_match_reference_naming():
+    keys = set(_field().state_dict().keys())
+    want = {
+        "aabb", "max_res", "num_levels", "log2_hashmap_size", "embedding_appearance.embedding.weight",
+        "mlp_base_grid.hash_table", "mlp_base.0.hash_table",
+        "mlp_base_mlp.layers.0.weight", "mlp_base_mlp.layers.0.bias", "mlp_base_mlp.layers.1.weight", "mlp_base_mlp.layers.1.bias",
+        "mlp_base.1.layers.0.weight", "mlp_base.1.layers.0.bias", "mlp_base.1.layers.1.weight", "mlp_base.1.layers.1.bias",
+        "mlp_semantics.layers.0.weight", "mlp_semantics.layers.0.bias", "mlp_semantics.layers.1.weight", "mlp_semantics.layers.1.bias",
+        "field_head_semantics.net.weight", "field_head_semantics.net.bias",
+        "mlp_head.layers.0.weight", "mlp_head.layers.0.bias", "mlp_head.layers.1.weight", "mlp_head.layers.1.bias",
+        "mlp_head.layers.2.weight", "mlp_head.layers.2.bias",
+    }
+    assert keys == want
+    f = _field()
+    f2 = _field()
+    f2.load_state_dict(f.state_dict(), strict=True)  # fruit_pipeline.py:240
+    assert torch.equal(f2.mlp_base_grid.hash_table, f.mlp_base_grid.hash_table)
+
+
+def test_field_shapes_and_scalings_follow_reference_defaults():
+    f = _field()
+    shp = f.kernel_shape()
+    assert shp.base_dims == [32, 64, 16] and shp.semantic_dims == [15, 64, 64] and shp.color_dims == [63, 64, 64, 3]
+    assert list(shp.scalings) == ns.hash_scalings(16, 16, 2048).tolist()
+    big = _field(geo_feat_dim=30, num_layers_semantic=3, hidden_dim_semantics=128, max_res=4096)
+    assert big.kernel_shape().semantic_dims == [30, 128, 128, 64] and big.kernel_shape().color_dims == [78, 64, 64, 3]
+    assert f.position_mode() == 0 and f.train().appearance_mode() == 0 and f.eval().appearance_mode() == 2
+    f.test_mode = "export"
+    assert f.appearance_mode() == 1
+
+
+def test_holders_have_no_python_forward():
+    f = _field()
+    with pytest.raises(RuntimeError, match="no PyTorch fallback"):
+        f.mlp_base_mlp(torch.zeros(1, 32))
+
+
+def test_method_configs_carry_reference_hyperparameters():
+    small, big, huge = METHODS["fruit_nerf"], METHODS["fruit_nerf_big"], METHODS["fruit_nerf_huge"]
+    assert small.max_num_iterations == 30000 and small.pipeline.datamanager.train_num_rays_per_batch == 4096
+    assert big.pipeline.model.log2_hashmap_size == 21 and big.pipeline.model.max_res == 4096 and big.pipeline.model.geo_feat_dim == 30
+    assert big.pipeline.model.num_nerf_samples_per_ray == 128 and huge.pipeline.model.num_nerf_samples_per_ray == 64
+    assert huge.pipeline.model.max_res == 8192 and huge.pipeline.datamanager.train_num_rays_per_batch == 16384
+    assert small.optimizers["fields"]["optimizer"]["type"] == "Adam" and big.optimizers["fields"]["optimizer"]["type"] == "RAdam"
+    assert FruitNerfModel is FruitModel
+
+
+def test_model_requires_semantics_metadata_and_builds():
+    cfg = FruitNerfModelConfig()
+    sem = Semantics(filenames=[], classes=["fruit"], colors=torch.tensor([[0.0, 0, 0], [1.0, 0, 0]]))
+    with pytest.raises(AssertionError):
+        FruitModel(cfg, metadata={}, scene_box=SceneBox(torch.tensor([[-1.0, -1, -1], [1, 1, 1]])), num_train_data=3, test_mode="val")
+    cfg.log2_hashmap_size = 10
+    m = FruitModel(cfg, metadata={"semantics": sem}, scene_box=SceneBox(torch.tensor([[-1.0, -1, -1], [1, 1, 1]])), num_train_data=3,
+                   test_mode="val")
+    assert set(m.get_param_groups().keys()) == {"proposal_networks", "fields"}
+    assert len(m.get_param_groups()["fields"]) == len(list(m.field.parameters()))
+    m.setup_inference(render_rgb=True, num_inference_samples=20)
+    assert isinstance(m.proposal_sampler, UniformSamplerWithNoise) and m.field.spatial_distortion is None
+    rb = RayBundle(origins=torch.zeros(4, 3), directions=torch.ones(4, 3))
+    rb = m.collider(rb)
+    assert torch.all(rb.nears == 0.05) and torch.all(rb.fars == 1000.0)
+
+
+def test_export_grid_matches_oracle_restatement():
+    for n, aabb in ((6, ((-1, -1, -1), (1, 1, 1))), (10, ((-1.0, -0.5, -0.25), (1.0, 0.5, 0.75)))):
+        corners = get_corners_of_aabb(aabb, "cpu")
+        pts, plane = sample_surface_points(corners, n, "cpu")
+        pts_ref, plane_ref = ns.surface_points(aabb, n)
+        assert torch.equal(pts, pts_ref) and torch.equal(plane, plane_ref)
+    dm = FruitDataManager(FruitDataManagerConfig(eval_num_rays_per_batch=10), device="cpu")
+    assert dm.setup_inference(aabb=((-1, -1, -1), (1, 1, 1)), num_points=5) == 25
+    sizes = []
+    for _ in range(3):
+        rb, _ = dm.next_sample_volume(0)
+        sizes.append(len(rb))
+        assert torch.all(rb.nears == 0) and torch.allclose(rb.fars, torch.full_like(rb.fars, 2.0))
+        assert torch.allclose(rb.directions, torch.tensor([[0.0, 0.0, 1.0]]).expand(len(rb), 3))
+    assert sizes == [10, 10, 5]
+
+
+def test_samplers_match_oracle_bins():
+    rb = RayBundle(origins=torch.zeros(3, 3), directions=torch.ones(3, 3), nears=torch.zeros(3, 1), fars=torch.full((3, 1), 2.0))
+    s = UniformSamplerWithNoise(num_samples=7).eval()(rb)
+    st, en = ns.uniform_bins(rb.nears, rb.fars, 7)
+    assert torch.equal(s.frustums.starts, st) and torch.equal(s.frustums.ends, en)
+    assert torch.equal(s.deltas, en - st) and s.frustums.origins.shape == (3, 7, 3)
+    p = UniformLinDispPiecewiseSampler(num_samples=8).eval()(RayBundle(origins=torch.zeros(2, 3), directions=torch.ones(2, 3),
+                                                                     nears=torch.full((2, 1), 0.05), fars=torch.full((2, 1), 1000.0)))
+    e = torch.cat([p.frustums.starts[0, :, 0], p.frustums.ends[0, -1:, 0]])
+    assert abs(float(e[0]) - 0.05) < 1e-6 and abs(float(e[-1]) - 1000.0) < 0.1 and bool((e[1:] > e[:-1]).all())
+
+
+def test_ply_writer_roundtrip(tmp_path):
+    pts = np.array([[0.0, 1.0, 2.0], [3.0, 4.0, 5.0]])
+    col = np.array([[1.0, 0.5, 0.0], [0.0, 0.0, 1.0]])
+    path = tmp_path / "a" / "cloud.ply"
+    write_ply(path, pts, col)
+    raw = path.read_bytes()
+    head, body = raw.split(b"end_header\n")
+    assert b"element vertex 2" in head and b"property double x" in head and b"property uchar red" in head
+    rec = np.frombuffer(body, dtype=[("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("r", "u1"), ("g", "u1"), ("b", "u1")])
+    assert np.allclose(np.stack([rec["x"], rec["y"], rec["z"]], -1), pts) and rec["r"].tolist() == [255, 0] and rec["g"][0] == 127
+
+
+WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from fruitnerf_b200 import ops
+from fruitnerf_b200.fruit_pipeline import sync_gradients
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+params = [torch.zeros(5, 2), torch.zeros(3), torch.zeros(7, 7)]
+flat, views = ops.flat_zero_grads(params)
+assert flat.numel() == 12 + 4 + 52 and all(v.data_ptr() % 16 == 0 for v in views)
+for i, v in enumerate(views):
+    v += float(rank + 1) * (i + 1)       # what the backward kernels would have accumulated
+sync_gradients(flat, world)
+for i, v in enumerate(views):
+    want = (i + 1) * sum(r + 1 for r in range(world)) / world   # DDP mean
+    assert torch.allclose(v, torch.full_like(v, want)), (rank, i, v)
+# ray sharding: rank r owns rays [r*R, (r+1)*R) of the global batch, no overlap, full cover
+R = 8
+own = torch.arange(rank * R, (rank + 1) * R)
+allr = [torch.zeros(R, dtype=torch.long) for _ in range(world)]
+dist.all_gather(allr, own)
+assert torch.equal(torch.cat(allr), torch.arange(world * R))
+dist.barrier()
+print("rank", rank, "ok")
+"""
+
+
+def test_flat_gradient_allreduce_world2_gloo(tmp_path):
+    """N>1 path on CPU: flat gradient buffer + mean all-reduce (the DDP exchange of
+    fruit_pipeline.py:117) and the per-rank ray partition, world_size 2 over gloo."""
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), str(ROOT)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0, out
