@@ -165,7 +165,7 @@ def run_ours(args):
         one_step(batch)
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if (rank == 0 and not args.no_clocks) else None
     if world > 1:
         import torch.distributed as dist
 
@@ -175,7 +175,8 @@ def run_ours(args):
         sampler.start()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     for i in range(args.steps):
-        flush.fill_(float(i))  # evict the table / weights from L2 between timed steps
+        if not args.no_flush:
+            flush.fill_(float(i))  # evict the table / weights from L2 between timed steps
         one_step(batch, evs[i])
     torch.cuda.synchronize()
     if world > 1:
@@ -201,7 +202,7 @@ def run_ours(args):
     for i in range(e2e_steps):
         b = [t.to(dev, non_blocking=True) for t in host]
         loss = one_step(b)
-        _ = float(loss)  # D2H
+        _ = float(loss.detach())  # D2H
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
@@ -344,6 +345,8 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--cpu-rays", type=int, default=2048)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="diagnostic: skip the L2 flush between timed steps")
+    ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample nvidia-smi during the timed region")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
