@@ -265,7 +265,16 @@ int fnr_render_backward(const fnr_field_desc* desc, const fnr_field_params* para
                   point_grads,
                   desc->pass_semantic_gradients};
   if ((rc = launch_simt_composite_backward(Rr, B, st))) return rc;
-  KFieldBwd FB{point_grads, saved->stash_encoding};
+  KFieldBwd FB{point_grads, saved->stash_encoding, saved->sample_rgb};
+  int impl = desc->impl;
+  if (impl == FNR_IMPL_AUTO) impl = tc_backward_supported(fam, F, Rr, FB) ? FNR_IMPL_TCGEN05 : FNR_IMPL_SIMT;
+  if (impl == FNR_IMPL_TCGEN05) {
+    if (!tc_backward_supported(fam, F, Rr, FB)) {
+      set_error("tcgen05 backward kernel does not support this configuration");
+      return FNR_ERR_UNSUPPORTED;
+    }
+    return launch_tc_field_backward(fam, F, P, G, Rr, FB, st);
+  }
   return launch_simt_field_backward(fam, F, P, G, Rr, FB, st);
 }
 

@@ -75,6 +75,7 @@ struct KCompositeBwd {
 struct KFieldBwd {
   const float* point_grads;     // [N,5]
   const float* stash_encoding;  // [N,32] or NULL (recompute)
+  const float* sample_rgb;      // [N,3] forward rgb (tcgen05 backward: sigmoid' without re-running colour2)
 };
 
 struct KExport {
@@ -110,5 +111,10 @@ int launch_hash_indices(const KField& F, const KRays& Rr, int32_t* rows, float* 
 bool tc_supported(Family fam, const KField& F, const KRays& Rr);
 int launch_tc_render_forward(Family fam, const KField& F, const KParams& P, const KRays& Rr, const KFieldOut& O,
                              const KComposite& Cm, cudaStream_t st);
+
+// tensor-core field backward (fnr_tc_bwd.cu)
+bool tc_backward_supported(Family fam, const KField& F, const KRays& Rr, const KFieldBwd& B);
+int launch_tc_field_backward(Family fam, const KField& F, const KParams& P, const KParams& G, const KRays& Rr, const KFieldBwd& B,
+                             cudaStream_t st);
 
 }  // namespace fnr

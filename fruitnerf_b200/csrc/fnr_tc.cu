@@ -23,9 +23,11 @@
 #include "fnr_common.cuh"
 #include "fnr_kernels.h"
 #include "fnr_tcgen05.cuh"
+#include "fnr_tc_common.cuh"
 
 namespace fnr {
 using namespace tc;
+using namespace tcx;
 
 namespace {
 
@@ -33,7 +35,7 @@ constexpr int kSlots = 2;
 constexpr int kCtaThreads = kSlots * 128;
 constexpr int kMaxGroupPoints = 768;
 constexpr int kTmemColsPerSlot = 160;
-constexpr unsigned kFullMask = 0xffffffffu;
+constexpr unsigned kFullMask = kTcFullMask;
 
 // ---- small-family dimensions -------------------------------------------------------------------
 constexpr int GEO = 15, ENC = 32, H = 64, APP = 32, SHD = 16;
@@ -47,7 +49,6 @@ constexpr int K_COL1 = 64, N_COL1 = 64;
 constexpr int K_COL2 = 64, N_COL2 = 16;
 
 // shared-memory map (bytes).  Weight tiles: hi then lo, canonical layout with ROWS = N.
-constexpr int wbytes(int n, int k) { return n * k * 2; }
 constexpr int OFF_W_BASE0 = 0;
 constexpr int OFF_W_BASE1 = OFF_W_BASE0 + 2 * wbytes(N_BASE0, K_BASE0);
 constexpr int OFF_W_SEM0 = OFF_W_BASE1 + 2 * wbytes(N_BASE1, K_BASE1);
@@ -72,71 +73,6 @@ static_assert(OFF_TILES % 16 == 0 && SLOT_TILE_BYTES % 16 == 0 && OFF_BIAS % 16 
 constexpr int C_R0 = 0;    // 64 cols: base0 out, later colour0 out, colour1 out
 constexpr int C_R1 = 64;   // 16 cols: base1 out, later semantic-head out, colour2 out
 constexpr int C_R2 = 80;   // 64 cols: semantic0 out
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// Stage W[N][K] (fp32, torch layout, optional column permutation / row padding) into the canonical
-// bf16 hi/lo tiles.  getw(n, k) returns the fp32 weight of padded position (n, k).
-template <int NP, int KP, class F>
-__device__ __forceinline__ void stage_weight(uint8_t* tile, F getw) {
-  for (int idx = threadIdx.x; idx < NP * KP; idx += kCtaThreads) {
-    const int n = idx / KP, k = idx % KP;
-    float hi, lo;
-    split_bf16(getw(n, k), hi, lo);
-    const int off = (k >> 3) * (NP * 16) + n * 16 + (k & 7) * 2;
-    *reinterpret_cast<__nv_bfloat16*>(tile + off) = __float2bfloat16_rn(hi);
-    *reinterpret_cast<__nv_bfloat16*>(tile + wbytes(NP, KP) + off) = __float2bfloat16_rn(lo);
-  }
-}
-
-// Store 8 consecutive K elements of this thread's row (chunk j) as hi/lo bf16.
-__device__ __forceinline__ void store_chunk(uint8_t* tile_hi, int lo_off, int row, int j, const float (&v)[8]) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float h0, l0, h1, l1;
-    split_bf16(v[2 * q], h0, l0);
-    split_bf16(v[2 * q + 1], h1, l1);
-    h[q] = pack_bf16x2(h0, h1);
-    l[q] = pack_bf16x2(l0, l1);
-  }
-  uint8_t* p = tile_hi + j * (128 * 16) + row * 16;
-  *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
-  *reinterpret_cast<uint4*>(p + lo_off) = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
-// Issue the 3-way split GEMM D[128,N] = A[128,K] W[N,K]^T (one thread).
-template <int K, int N>
-__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_hi, uint32_t w_hi) {
-  constexpr uint32_t idesc = idesc_bf16_f32(128, N);
-  constexpr uint32_t a_lo_off = 128 * K * 2, w_lo_off = N * K * 2;
-#pragma unroll
-  for (int ks = 0; ks < K / 16; ++ks) {
-    const uint64_t ah = smem_desc(a_hi + ks * 2 * 128 * 16, 128 * 16, 128);
-    const uint64_t al = smem_desc(a_hi + a_lo_off + ks * 2 * 128 * 16, 128 * 16, 128);
-    const uint64_t wh = smem_desc(w_hi + ks * 2 * N * 16, N * 16, 128);
-    const uint64_t wl = smem_desc(w_hi + w_lo_off + ks * 2 * N * 16, N * 16, 128);
-    mma_ss(d_tmem, ah, wh, idesc, ks > 0);
-    mma_ss(d_tmem, al, wh, idesc, true);
-    mma_ss(d_tmem, ah, wl, idesc, true);
-  }
-}
-
-__device__ __forceinline__ float warp_incl_scan_f(float v, int lane) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const float t = __shfl_up_sync(kFullMask, v, o);
-    if (lane >= o) v += t;
-  }
-  return v;
-}
-__device__ __forceinline__ float warp_sum_f(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
-  return v;
-}
 
 struct TcArgs {
   KField F;
@@ -168,26 +104,26 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
     for (int i = 0; i < kSlots; ++i) mbar_init(&s_bar[i], 1);
     mbar_fence_init();
   }
-  stage_weight<N_BASE0, K_BASE0>(smem + OFF_W_BASE0, [&](int n, int k) { return __ldg(P.base_w[0] + n * ENC + k); });
-  stage_weight<N_BASE1, K_BASE1>(smem + OFF_W_BASE1, [&](int n, int k) { return __ldg(P.base_w[1] + n * H + k); });
-  stage_weight<N_SEM0, K_SEM0>(smem + OFF_W_SEM0, [&](int n, int k) { return k < GEO ? __ldg(P.sem_w[0] + n * GEO + k) : 0.f; });
+  stage_weight<kCtaThreads, N_BASE0, K_BASE0>(smem + OFF_W_BASE0, [&](int n, int k) { return __ldg(P.base_w[0] + n * ENC + k); });
+  stage_weight<kCtaThreads, N_BASE1, K_BASE1>(smem + OFF_W_BASE1, [&](int n, int k) { return __ldg(P.base_w[1] + n * H + k); });
+  stage_weight<kCtaThreads, N_SEM0, K_SEM0>(smem + OFF_W_SEM0, [&](int n, int k) { return k < GEO ? __ldg(P.sem_w[0] + n * GEO + k) : 0.f; });
   // fold: logit = head_w . (W1 z + b1) + head_b  =>  row 0 of the N=16 tile is head_w^T W1
-  stage_weight<N_SEMH, K_SEMH>(smem + OFF_W_SEMH, [&](int n, int k) {
+  stage_weight<kCtaThreads, N_SEMH, K_SEMH>(smem + OFF_W_SEMH, [&](int n, int k) {
     if (n != 0) return 0.f;
     float acc = 0.f;
     for (int j = 0; j < H; ++j) acc = fmaf(__ldg(P.head_w + j), __ldg(P.sem_w[1] + j * H + k), acc);
     return acc;
   });
   // colour layer 0 with the K order [sh | app | geo | 0] (torch order is [sh | geo | app])
-  stage_weight<N_COL0, K_COL0>(smem + OFF_W_COL0, [&](int n, int k) {
+  stage_weight<kCtaThreads, N_COL0, K_COL0>(smem + OFF_W_COL0, [&](int n, int k) {
     const float* w = P.col_w[0] + n * (SHD + GEO + APP);
     if (k < SHD) return __ldg(w + k);
     if (k < SHD + APP) return __ldg(w + SHD + GEO + (k - SHD));
     if (k < SHD + APP + GEO) return __ldg(w + SHD + (k - SHD - APP));
     return 0.f;
   });
-  stage_weight<N_COL1, K_COL1>(smem + OFF_W_COL1, [&](int n, int k) { return __ldg(P.col_w[1] + n * H + k); });
-  stage_weight<N_COL2, K_COL2>(smem + OFF_W_COL2, [&](int n, int k) { return n < 3 ? __ldg(P.col_w[2] + n * H + k) : 0.f; });
+  stage_weight<kCtaThreads, N_COL1, K_COL1>(smem + OFF_W_COL1, [&](int n, int k) { return __ldg(P.col_w[1] + n * H + k); });
+  stage_weight<kCtaThreads, N_COL2, K_COL2>(smem + OFF_W_COL2, [&](int n, int k) { return n < 3 ? __ldg(P.col_w[2] + n * H + k) : 0.f; });
   for (int i = tid; i < B_COUNT; i += kCtaThreads) {
     float v = 0.f;
     if (i < B_BASE1) v = __ldg(P.base_b[0] + i);

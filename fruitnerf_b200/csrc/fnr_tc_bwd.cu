@@ -1,0 +1,669 @@
+// Field backward on the 5th-gen tensor cores (sm_100a): for each tile of 128 sample points
+//   recompute the activations (5 GEMM round trips, as the fused forward),
+//   back-propagate through the colour / semantic / base MLPs   dX = dY W        (W read MN-major from the
+//                                                                              same tile the forward uses),
+//   accumulate every weight gradient                           dW = dY^T X      (both activation tiles read
+//                                                                              MN-major; M=64 accumulators
+//                                                                              RESIDENT in TMEM for the whole
+//                                                                              kernel, flushed once per CTA),
+//   scatter the encoding gradient into the hash-table gradient (red.global.add.v2.f32).
+// Autograd semantics of fruit_nerf/fruit_field.py:168-281 (semantic branch sees detach(geo), trunc_exp
+// backward clamps the exponent to [-15, 15]); upstream per-sample gradients come from the compositing
+// backward (simt_composite_backward_kernel).
+//
+// One persistent CTA of 128 threads per SM: thread r owns point r of the tile (TMEM lane r).  All operands
+// are bf16 hi/lo splits (3 MMAs per K-step, ~2^-16 per product); the K=16 "[geo | 1]" operand of the
+// semantic branch is chunks 6-7 of the colour-input tile, so no activation is stored twice.
+// Bias gradients come for free from constant-1 columns (padding columns of the geo / colour-input tiles,
+// a 128x16 ONES tile for the K-exact layers) or from per-thread running sums (3- and 16-wide layers).
+#include "fnr_common.cuh"
+#include "fnr_kernels.h"
+#include "fnr_tc_common.cuh"
+
+namespace fnr {
+using namespace tc;
+using namespace tcx;
+
+namespace {
+
+constexpr int kT = 128;  // threads per CTA
+constexpr int GEO = 15, ENC = 32, H = 64, APP = 32, SHD = 16;
+
+// ---- shared-memory map (bytes) ------------------------------------------------------------------
+constexpr int OFF_W0 = 0;                                  // [64 rows][32]  hi,lo
+constexpr int OFF_W1 = OFF_W0 + 2 * wbytes(64, 32);        // [16][64]
+constexpr int OFF_WS0 = OFF_W1 + 2 * wbytes(16, 64);       // [64][16]
+constexpr int OFF_WC0 = OFF_WS0 + 2 * wbytes(64, 16);      // [64][64], K order [sh|app|geo|0]
+constexpr int OFF_WC1 = OFF_WC0 + 2 * wbytes(64, 64);      // [64][64]
+constexpr int OFF_WC2 = OFF_WC1 + 2 * wbytes(64, 64);      // [16][64]
+constexpr int OFF_F32 = OFF_WC2 + 2 * wbytes(16, 64);
+// fp32 block: b0[64] b1[16] bs0[64] bc0[64] bc1[64] fold[64] reduce scratch[64]
+constexpr int F_B0 = 0, F_B1 = 64, F_BS0 = 80, F_BC0 = 144, F_BC1 = 208, F_FOLD = 272, F_RED = 336, F_COUNT = 416;  // F_RED: v[64] + 4 per-warp partial sums
+constexpr int TILE64 = 2 * 128 * 64 * 2;                   // 32 KB: K=64 tile, hi then lo
+constexpr int OFF_H = OFF_F32 + F_COUNT * 4;               // h1 (hi | lo)
+constexpr int OFF_CIN = OFF_H + TILE64;                    // colour input [sh | app | geo | 1]; chunks 6,7 double as the
+                                                           // K=16 "[geo | 1]" tile of the semantic branch
+constexpr int OFF_A = OFF_CIN + TILE64;                    // enc (K=32) -> z1 -> c2 -> enc again
+constexpr int OFF_C1 = OFF_A + TILE64;
+constexpr int OFF_DY = OFF_C1 + TILE64;
+constexpr int OFF_ONES = OFF_DY + TILE64;                  // [128][16] bf16, column 0 = 1
+constexpr int OFF_D16 = OFF_ONES + 128 * 16 * 2;           // 16-wide dY tile (hi 4 KB, lo 4 KB)
+constexpr int OFF_END = OFF_D16 + 2 * 128 * 16 * 2;
+constexpr int kSmem = OFF_END;
+constexpr int GEO_CHUNK = 6 * 2048;                        // byte offset of chunk 6 inside a K=64 tile half
+static_assert(kSmem + 64 <= 227 * 1024, "shared-memory budget");
+static_assert(OFF_H % 16 == 0 && OFF_D16 % 16 == 0, "tile alignment");
+
+// ---- tensor-memory map (columns) ----------------------------------------------------------------
+constexpr int C_R0 = 0, C_R1 = 64, C_R2 = 80;              // work regions (64, 16, 64)
+constexpr int C_AV = 144;    // z1^T dlogit            [64 x 16]
+constexpr int C_AS0 = 160;   // dz1^T [geo|1]          [64 x 16]
+constexpr int C_AC2 = 176;   // c2^T do3               [64 x 16]
+constexpr int C_AC1 = 192;   // dc2^T c1               [64 x 64]
+constexpr int C_AC1B = 256;  // dc2^T ones             [64 x 16]
+constexpr int C_AC0 = 272;   // dc1^T cin              [64 x 64]
+constexpr int C_AB1 = 336;   // h1^T dout16            [64 x 16]
+constexpr int C_AB0 = 352;   // dh1^T enc              [64 x 32]
+constexpr int C_AB0B = 384;  // dh1^T ones             [64 x 16]
+
+__host__ __device__ constexpr uint32_t idesc_mn(int M, int N, int a_mn, int b_mn) {
+  return idesc_bf16_f32(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
+}
+
+// dX[128, NOUT] = dY[128, KR] * W[KR rows, NOUT cols]   (A K-major, B MN-major view of the forward tile)
+template <int KR, int NOUT>
+__device__ __forceinline__ void issue_dx(uint32_t d_tmem, uint32_t a_hi, uint32_t w_hi) {
+  constexpr uint32_t idesc = idesc_mn(128, NOUT, 0, 1);
+  constexpr uint32_t a_lo = 128 * KR * 2, w_lo = KR * NOUT * 2;
+#pragma unroll
+  for (int ks = 0; ks < KR / 16; ++ks) {
+    const uint64_t ah = smem_desc(a_hi + ks * 4096, 2048, 128);
+    const uint64_t al = smem_desc(a_hi + a_lo + ks * 4096, 2048, 128);
+    const uint64_t wh = smem_desc(w_hi + ks * 256, 128, KR * 16);
+    const uint64_t wl = smem_desc(w_hi + w_lo + ks * 256, 128, KR * 16);
+    mma_ss(d_tmem, ah, wh, idesc, ks > 0);
+    mma_ss(d_tmem, al, wh, idesc, true);
+    mma_ss(d_tmem, ah, wl, idesc, true);
+  }
+}
+
+// ACC[FA=64, FB] (+)= A[128, 64]^T * B[128, FB]   (both row-per-point tiles read MN-major, K = 128 points).
+// a_lo / b_lo: shared addresses of the lo halves (0 = operand not split).
+template <int FB>
+__device__ __forceinline__ void issue_dw(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, bool accumulate) {
+  constexpr uint32_t idesc = idesc_mn(64, FB, 1, 1);
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const uint64_t ah = smem_desc(a_hi + ks * 256, 128, 2048);
+    const uint64_t bh = smem_desc(b_hi + ks * 256, 128, 2048);
+    mma_ss(d_tmem, ah, bh, idesc, accumulate || ks > 0);
+    if (a_lo) mma_ss(d_tmem, smem_desc(a_lo + ks * 256, 128, 2048), bh, idesc, true);
+    if (b_lo) mma_ss(d_tmem, ah, smem_desc(b_lo + ks * 256, 128, 2048), idesc, true);
+  }
+}
+
+// Read this thread's 64 accumulator columns (+ bias), optional ReLU.
+template <bool RELU>
+__device__ __forceinline__ void load_row64(uint32_t taddr, const float* bias, float (&v)[64]) {
+  uint32_t r0[32], r1[32];
+  tmem_ld32(taddr, r0);
+  tmem_ld32(taddr + 32, r1);
+  tmem_ld_wait();
+#pragma unroll
+  for (int n = 0; n < 64; ++n) {
+    float x = __uint_as_float(n < 32 ? r0[n] : r1[n - 32]);
+    if (bias) x += bias[n];
+    v[n] = RELU ? fmaxf(x, 0.f) : x;
+  }
+}
+
+__device__ __forceinline__ void store_row64(uint8_t* tile, int row, const float (&v)[64]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float c[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) c[q] = v[8 * j + q];
+    store_chunk(tile, 128 * 64 * 2, row, j, c);
+  }
+}
+
+// ReLU mask of a stored 64-wide tile row (hi half): bit n set iff activation n > 0.
+__device__ __forceinline__ unsigned long long relu_mask64(const uint8_t* tile_hi, int row) {
+  unsigned long long m = 0ull;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint4 u = *reinterpret_cast<const uint4*>(tile_hi + j * 2048 + row * 16);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      // bf16 > 0  <=>  non-zero magnitude and sign bit clear (activations are relu outputs: never negative)
+      if (w[q] & 0x7FFFu) m |= 1ull << (8 * j + 2 * q);
+      if (w[q] & 0x7FFF0000u) m |= 1ull << (8 * j + 2 * q + 1);
+    }
+  }
+  return m;
+}
+
+struct BwdArgs {
+  KField F;
+  KParams P;
+  KParams G;
+  KRays Rr;
+  const float* point_grads;     // [N,5]  d_density, d_rgb[3], d_logit
+  const float* stash_encoding;  // [N,32]
+  const float* sample_rgb;      // [N,3]
+};
+
+__global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_constant__ BwdArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t s_bar;
+  __shared__ uint32_t s_tmem_base;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = tid;
+  const KParams& P = a.P;
+  const KParams& G = a.G;
+  const KField& F = a.F;
+  float* sf = reinterpret_cast<float*>(smem + OFF_F32);
+
+  if (warp == 0) tmem_alloc(&s_tmem_base, 512);
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+  }
+  stage_weight<kT, 64, 32>(smem + OFF_W0, [&](int n, int k) { return __ldg(P.base_w[0] + n * ENC + k); });
+  stage_weight<kT, 16, 64>(smem + OFF_W1, [&](int n, int k) { return __ldg(P.base_w[1] + n * H + k); });
+  stage_weight<kT, 64, 16>(smem + OFF_WS0, [&](int n, int k) { return k < GEO ? __ldg(P.sem_w[0] + n * GEO + k) : 0.f; });
+  stage_weight<kT, 64, 64>(smem + OFF_WC0, [&](int n, int k) {
+    const float* w = P.col_w[0] + n * (SHD + GEO + APP);
+    if (k < SHD) return __ldg(w + k);
+    if (k < SHD + APP) return __ldg(w + SHD + GEO + (k - SHD));
+    if (k < SHD + APP + GEO) return __ldg(w + SHD + (k - SHD - APP));
+    return 0.f;
+  });
+  stage_weight<kT, 64, 64>(smem + OFF_WC1, [&](int n, int k) { return __ldg(P.col_w[1] + n * H + k); });
+  stage_weight<kT, 16, 64>(smem + OFF_WC2, [&](int n, int k) { return n < 3 ? __ldg(P.col_w[2] + n * H + k) : 0.f; });
+  for (int i = tid; i < F_COUNT; i += kT) {
+    float v = 0.f;
+    if (i < F_B1) v = __ldg(P.base_b[0] + i);
+    else if (i < F_BS0) v = __ldg(P.base_b[1] + (i - F_B1));
+    else if (i < F_BC0) v = __ldg(P.sem_b[0] + (i - F_BS0));
+    else if (i < F_BC1) v = __ldg(P.col_b[0] + (i - F_BC0));
+    else if (i < F_FOLD) v = __ldg(P.col_b[1] + (i - F_BC1));
+    else if (i < F_RED) {  // fold[k] = sum_j head_w[j] * W_sem1[j][k]
+      const int k = i - F_FOLD;
+      float acc = 0.f;
+      for (int j = 0; j < H; ++j) acc = fmaf(__ldg(P.head_w + j), __ldg(P.sem_w[1] + j * H + k), acc);
+      v = acc;
+    }
+    sf[i] = v;
+  }
+  {  // ONES tile: column 0 = 1 (bf16 0x3F80), everything else 0
+    uint8_t* ones = smem + OFF_ONES;
+    *reinterpret_cast<uint4*>(ones + row * 16) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(ones + 2048 + row * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+
+  const uint32_t tb = s_tmem_base;
+  const uint32_t trow = tb + ((uint32_t)(warp * 32) << 16);
+  uint8_t* tH = smem + OFF_H;
+  uint8_t* tD16 = smem + OFF_D16;
+  uint8_t* tCIN = smem + OFF_CIN;
+  uint8_t* tA = smem + OFF_A;
+  uint8_t* tC1 = smem + OFF_C1;
+  uint8_t* tDY = smem + OFF_DY;
+  const uint32_t sb = smem_u32(smem);
+  const uint32_t aH = sb + OFF_H, aD16 = sb + OFF_D16, aCIN = sb + OFF_CIN, aA = sb + OFF_A, aC1 = sb + OFF_C1,
+                 aDY = sb + OFF_DY, aONES = sb + OFF_ONES;
+  constexpr uint32_t LO64 = 128 * 64 * 2, LO32 = 128 * 32 * 2, LO16 = 128 * 16 * 2;
+  const uint32_t aGEO = aCIN + GEO_CHUNK;  // [geo | 1] as a K=16 tile: hi at aGEO, lo at aGEO + LO64
+  uint32_t phase = 0;
+  const bool issuer = tid == 0;
+
+  const long long N = (long long)a.Rr.R * a.Rr.S;
+  const long long tiles = (N + kT - 1) / kT;
+  const int S = a.Rr.S;
+  const uint32_t hmask = (1u << F.log2T) - 1u;
+
+  // per-thread running sums of the narrow bias gradients
+  float acc_do3[3] = {0.f, 0.f, 0.f}, acc_dout[16], acc_dlogit = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc_dout[i] = 0.f;
+  bool first = true;
+
+#define FNR_SYNC_ISSUE(...)            \
+  fence_async_smem();                  \
+  fence_before_sync();                 \
+  __syncthreads();                     \
+  if (issuer) {                        \
+    fence_after_sync();                \
+    __VA_ARGS__;                       \
+    mma_commit(&s_bar);                \
+  }
+#define FNR_WAIT()          \
+  mbar_wait(&s_bar, phase); \
+  phase ^= 1;               \
+  fence_after_sync();
+
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long p = tile * kT + row;
+    const bool valid = p < N;
+    const long long pc = valid ? p : N - 1;
+    const int ray = (int)(pc / S);
+    const float* o = a.Rr.origins + 3 * (size_t)ray;
+    const float* d = a.Rr.directions + 3 * (size_t)ray;
+    bool sel;
+    const Vec3 pos = field_position(o, d, __ldg(a.Rr.starts + pc), __ldg(a.Rr.ends + pc), F.position_mode, F.aabb, sel);
+    const float vm = valid ? 1.f : 0.f;
+    const float* pg = a.point_grads + 5 * (size_t)pc;
+    const float d_sigma = __ldg(pg) * vm;
+    const float d_rgb[3] = {__ldg(pg + 1) * vm, __ldg(pg + 2) * vm, __ldg(pg + 3) * vm};
+    const float d_logit = __ldg(pg + 4) * vm;
+
+    // ---- T0: encoding tile (from the forward's stash) -> A ; base0 ------------------------------------
+    {
+      const float4* st = reinterpret_cast<const float4*>(a.stash_encoding + (size_t)pc * ENC);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 u = __ldg(st + 2 * j), w = __ldg(st + 2 * j + 1);
+        const float c[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
+        store_chunk(tA, 128 * 32 * 2, row, j, c);
+      }
+    }
+    FNR_SYNC_ISSUE(issue_gemm<32, 64>(tb + C_R0, aA, sb + OFF_W0))
+
+    // ---- T1: colour-input chunks [sh | app] ; h1 -> H ; base1 ------------------------------------------
+    int cam = 0;
+    {
+      float sh[SHD];
+      sh_degree4(__ldg(d), __ldg(d + 1), __ldg(d + 2), sh);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float c[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) c[q] = sh[8 * j + q];
+        store_chunk(tCIN, 128 * 64 * 2, row, j, c);
+      }
+      if (F.appearance_mode == FNR_APP_PER_CAMERA) {
+        cam = __ldg(a.Rr.camera_indices + ray);
+        const float4* e4 = reinterpret_cast<const float4*>(P.app_embedding + (size_t)cam * APP);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 u = __ldg(e4 + 2 * j), w = __ldg(e4 + 2 * j + 1);
+          const float c[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
+          store_chunk(tCIN, 128 * 64 * 2, row, 2 + j, c);
+        }
+      } else {  // FNR_APP_ZEROS
+        const float c[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) store_chunk(tCIN, 128 * 64 * 2, row, 2 + j, c);
+      }
+    }
+    FNR_WAIT()
+    {
+      float v[64];
+      load_row64<true>(trow + C_R0, sf + F_B0, v);
+      store_row64(tH, row, v);
+    }
+    FNR_SYNC_ISSUE(issue_gemm<64, 16>(tb + C_R1, aH, sb + OFF_W1))
+
+    // ---- T2: [h0 | geo] ; geo tiles ; dlogit tile ; semantic0 + colour0 --------------------------------
+    FNR_WAIT()
+    float d_h0;
+    {
+      uint32_t r0[16];
+      tmem_ld16(trow + C_R1, r0);
+      tmem_ld_wait();
+      float outv[16];
+#pragma unroll
+      for (int n = 0; n < 16; ++n) outv[n] = __uint_as_float(r0[n]) + sf[F_B1 + n];
+      // density = exp(h0) * selector ; trunc_exp backward: g * exp(clamp(h0, -15, 15))
+      d_h0 = sel ? d_sigma * expf(fminf(fmaxf(outv[0], -15.f), 15.f)) : 0.f;
+      float g0[8], g1[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        g0[q] = outv[1 + q];
+        g1[q] = q < 7 ? outv[9 + q] : 1.0f;  // column 15 / 63 = 1: bias-gradient column
+      }
+      store_chunk(tCIN, 128 * 64 * 2, row, 6, g0);
+      store_chunk(tCIN, 128 * 64 * 2, row, 7, g1);
+      const float dl0[8] = {d_logit, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      store_chunk(tD16, 128 * 16 * 2, row, 0, dl0);
+      store_chunk(tD16, 128 * 16 * 2, row, 1, z8);
+    }
+    FNR_SYNC_ISSUE(issue_gemm_lo<16, 64>(tb + C_R2, aGEO, aGEO + LO64, sb + OFF_WS0); issue_gemm<64, 64>(tb + C_R0, aCIN, sb + OFF_WC0))
+
+    // ---- T3: z1 -> A, c1 -> C1, dz1 -> DY ; colour1 + AV + AS0 ----------------------------------------
+    FNR_WAIT()
+    {
+      float v[64];
+      load_row64<true>(trow + C_R2, sf + F_BS0, v);
+      store_row64(tA, row, v);
+#pragma unroll
+      for (int n = 0; n < 64; ++n) v[n] = v[n] > 0.f ? d_logit * sf[F_FOLD + n] : 0.f;
+      store_row64(tDY, row, v);
+      load_row64<true>(trow + C_R0, sf + F_BC0, v);
+      store_row64(tC1, row, v);
+    }
+    FNR_SYNC_ISSUE(issue_gemm<64, 64>(tb + C_R0, aC1, sb + OFF_WC1); issue_dw<16>(tb + C_AV, aA, aA + LO64, aD16, aD16 + LO16, !first);
+                   issue_dw<16>(tb + C_AS0, aDY, aDY + LO64, aGEO, aGEO + LO64, !first))
+
+    // ---- T4: c2 -> A ; do3 -> D16 ; AC2 + dc2 -----------------------------------------------------------
+    FNR_WAIT()
+    float do3[3];
+    {
+      float v[64];
+      load_row64<true>(trow + C_R0, sf + F_BC1, v);
+      store_row64(tA, row, v);
+      const float* rgb = a.sample_rgb + 3 * (size_t)pc;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float c = __ldg(rgb + i);
+        do3[i] = d_rgb[i] * c * (1.0f - c);
+      }
+      const float c0[8] = {do3[0], do3[1], do3[2], 0.f, 0.f, 0.f, 0.f, 0.f}, z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      store_chunk(tD16, 128 * 16 * 2, row, 0, c0);
+      store_chunk(tD16, 128 * 16 * 2, row, 1, z8);
+    }
+    FNR_SYNC_ISSUE(issue_dw<16>(tb + C_AC2, aA, aA + LO64, aD16, aD16 + LO16, !first); issue_dx<16, 64>(tb + C_R2, aD16, sb + OFF_WC2))
+
+    // ---- T5: dc2 = (do3 Wc2) * relu'(c2) -> DY ; AC1, AC1b, dc1 ----------------------------------------
+    FNR_WAIT()
+    {
+      float v[64];
+      load_row64<false>(trow + C_R2, nullptr, v);
+      const unsigned long long m = relu_mask64(tA, row);
+#pragma unroll
+      for (int n = 0; n < 64; ++n) v[n] = ((m >> n) & 1ull) ? v[n] : 0.f;
+      store_row64(tDY, row, v);
+    }
+    FNR_SYNC_ISSUE(issue_dw<64>(tb + C_AC1, aDY, aDY + LO64, aC1, aC1 + LO64, !first); issue_dw<16>(tb + C_AC1B, aDY, aDY + LO64, aONES, 0u, !first);
+                   issue_dx<64, 64>(tb + C_R0, aDY, sb + OFF_WC1))
+
+    // ---- T6: dc1 = (dc2 Wc1) * relu'(c1) -> DY ; AC0, dcin --------------------------------------------
+    FNR_WAIT()
+    {
+      float v[64];
+      load_row64<false>(trow + C_R0, nullptr, v);
+      const unsigned long long m = relu_mask64(tC1, row);
+#pragma unroll
+      for (int n = 0; n < 64; ++n) v[n] = ((m >> n) & 1ull) ? v[n] : 0.f;
+      store_row64(tDY, row, v);
+    }
+    FNR_SYNC_ISSUE(issue_dw<64>(tb + C_AC0, aDY, aDY + LO64, aCIN, aCIN + LO64, !first); issue_dx<64, 64>(tb + C_R2, aDY, sb + OFF_WC0))
+
+    // ---- T7: dcin -> d_app (embedding gradient), d_geo ; dout16 -> D16 ; AB1, dh1 -----------------------
+    FNR_WAIT()
+    float dout[16];
+    {
+      float v[64];
+      load_row64<false>(trow + C_R2, nullptr, v);
+      if (F.appearance_mode == FNR_APP_PER_CAMERA) {
+        const bool uniform = __all_sync(kTcFullMask, cam == __shfl_sync(kTcFullMask, cam, 0));
+        if (uniform) {
+          // transposed butterfly: lane j ends with sum over the warp of d_app[j]
+          float w[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) w[i] = v[SHD + i];
+#pragma unroll
+          for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+            const bool hi = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (i < n) {
+                const float send = hi ? w[i] : w[i + n];
+                const float keep = hi ? w[i + n] : w[i];
+                w[i] = keep + __shfl_xor_sync(kTcFullMask, send, off);
+              }
+            }
+          }
+          if (w[0] != 0.f) atomicAdd(G.app_embedding + (size_t)cam * APP + lane, w[0]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < APP; ++i)
+            if (v[SHD + i] != 0.f) atomicAdd(G.app_embedding + (size_t)cam * APP + i, v[SHD + i]);
+        }
+      }
+      dout[0] = d_h0;
+#pragma unroll
+      for (int i = 0; i < GEO; ++i) dout[1 + i] = v[SHD + APP + i];
+      float c0[8], c1[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        c0[q] = dout[q];
+        c1[q] = dout[8 + q];
+      }
+      store_chunk(tD16, 128 * 16 * 2, row, 0, c0);
+      store_chunk(tD16, 128 * 16 * 2, row, 1, c1);
+    }
+    FNR_SYNC_ISSUE(issue_dw<16>(tb + C_AB1, aH, aH + LO64, aD16, aD16 + LO16, !first); issue_dx<16, 64>(tb + C_R0, aD16, sb + OFF_W1))
+
+    // ---- T8: dh1 = (dout W1) * relu'(h1) -> DY ; reload enc -> A ; AB0, AB0b, denc ------------------------
+    FNR_WAIT()
+    {
+      float v[64];
+      load_row64<false>(trow + C_R0, nullptr, v);
+      const unsigned long long m = relu_mask64(tH, row);
+#pragma unroll
+      for (int n = 0; n < 64; ++n) v[n] = ((m >> n) & 1ull) ? v[n] : 0.f;
+      store_row64(tDY, row, v);
+      const float4* st = reinterpret_cast<const float4*>(a.stash_encoding + (size_t)pc * ENC);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 u = __ldg(st + 2 * j), w = __ldg(st + 2 * j + 1);
+        const float c[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
+        store_chunk(tA, 128 * 32 * 2, row, j, c);
+      }
+    }
+    FNR_SYNC_ISSUE(issue_dw<32>(tb + C_AB0, aDY, aDY + LO64, aA, aA + LO32, !first); issue_dw<16>(tb + C_AB0B, aDY, aDY + LO64, aONES, 0u, !first);
+                   issue_dx<64, 32>(tb + C_R2, aDY, sb + OFF_W0))
+
+    // ---- T9: denc -> hash-table gradient scatter -------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < 3; ++i) acc_do3[i] += do3[i];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc_dout[i] += dout[i];
+    acc_dlogit += d_logit;
+    FNR_WAIT()
+    {
+      uint32_t r0[32];
+      tmem_ld32(trow + C_R2, r0);
+      tmem_ld_wait();
+      if (valid) {
+        float2* gt = reinterpret_cast<float2*>(G.hash_table);
+#pragma unroll 1
+        for (int l = 0; l < 16; ++l) {
+          const float g0 = __uint_as_float(r0[2 * l]), g1 = __uint_as_float(r0[2 * l + 1]);
+          if (g0 == 0.f && g1 == 0.f) continue;
+          const LevelCell c = level_cell(pos, F.scalings[l]);
+          const uint32_t base = (uint32_t)l << F.log2T;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float w = corner_weight(c, k);
+            if (w != 0.f) atomicAdd(gt + corner_row(c, k, hmask, base), make_float2(w * g0, w * g1));
+          }
+        }
+      }
+    }
+    fence_before_sync();  // this tile's TMEM reads are ordered before the next tile's MMAs (via the next barrier)
+    first = false;
+  }
+#undef FNR_SYNC_ISSUE
+#undef FNR_WAIT
+
+  // ---- flush the resident accumulators ---------------------------------------------------------------
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  if (!first) {
+    // M=64 accumulators: row i lives in TMEM lane (i % 16) + 32 * (i / 16)  ->  this thread: lane < 16, i = 16*warp + lane
+    const bool owner = lane < 16;
+    const int i = 16 * warp + lane;
+    uint32_t r[32];
+    // AV: v[i] = sum_points z1[i] * dlogit -> shared scratch
+    {
+      uint32_t q[8];
+      tmem_ld8(trow + C_AV, q);
+      tmem_ld_wait();
+      if (owner) sf[F_RED + i] = __uint_as_float(q[0]);
+    }
+    // AS0: d W_sem0[n=i][k<15], column 15 = d b_sem0[i]
+    {
+      uint32_t q[16];
+      tmem_ld16(trow + C_AS0, q);
+      tmem_ld_wait();
+      if (owner) {
+#pragma unroll
+        for (int k = 0; k < GEO; ++k) atomicAdd(G.sem_w[0] + i * GEO + k, __uint_as_float(q[k]));
+        atomicAdd(G.sem_b[0] + i, __uint_as_float(q[15]));
+      }
+    }
+    // AC2: rows = c2 feature k=i, cols = colour output n<3
+    {
+      uint32_t q[8];
+      tmem_ld8(trow + C_AC2, q);
+      tmem_ld_wait();
+      if (owner) {
+#pragma unroll
+        for (int n = 0; n < 3; ++n) atomicAdd(G.col_w[2] + n * H + i, __uint_as_float(q[n]));
+      }
+    }
+    // AC1 / AC1b
+    {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        tmem_ld32(trow + C_AC1 + 32 * half, r);
+        tmem_ld_wait();
+        if (owner) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) atomicAdd(G.col_w[1] + i * H + 32 * half + k, __uint_as_float(r[k]));
+        }
+      }
+      uint32_t q[8];
+      tmem_ld8(trow + C_AC1B, q);
+      tmem_ld_wait();
+      if (owner) atomicAdd(G.col_b[1] + i, __uint_as_float(q[0]));
+    }
+    // AC0: cols in [sh | app | geo | bias] order -> torch order [sh | geo | app]
+    {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        tmem_ld32(trow + C_AC0 + 32 * half, r);
+        tmem_ld_wait();
+        if (owner) {
+          float* gw = G.col_w[0] + i * (SHD + GEO + APP);
+#pragma unroll
+          for (int kk = 0; kk < 32; ++kk) {
+            const int k = 32 * half + kk;
+            const float val = __uint_as_float(r[kk]);
+            if (k < SHD) atomicAdd(gw + k, val);
+            else if (k < SHD + APP) atomicAdd(gw + SHD + GEO + (k - SHD), val);
+            else if (k < SHD + APP + GEO) atomicAdd(gw + SHD + (k - SHD - APP), val);
+            else atomicAdd(G.col_b[0] + i, val);
+          }
+        }
+      }
+    }
+    // AB1: rows = h1 feature k=i, cols = base output n<16
+    {
+      uint32_t q[16];
+      tmem_ld16(trow + C_AB1, q);
+      tmem_ld_wait();
+      if (owner) {
+#pragma unroll
+        for (int n = 0; n < 16; ++n) atomicAdd(G.base_w[1] + n * H + i, __uint_as_float(q[n]));
+      }
+    }
+    // AB0 / AB0b
+    {
+      tmem_ld32(trow + C_AB0, r);
+      tmem_ld_wait();
+      if (owner) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) atomicAdd(G.base_w[0] + i * ENC + k, __uint_as_float(r[k]));
+      }
+      uint32_t q[8];
+      tmem_ld8(trow + C_AB0B, q);
+      tmem_ld_wait();
+      if (owner) atomicAdd(G.base_b[0] + i, __uint_as_float(q[0]));
+    }
+    // narrow bias gradients + sum of dlogit: warp reduce, then one atomic per warp
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+      const float s = warp_sum_f(acc_do3[n]);
+      if (lane == 0) atomicAdd(G.col_b[2] + n, s);
+    }
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+      const float s = warp_sum_f(acc_dout[n]);
+      if (lane == 0) atomicAdd(G.base_b[1] + n, s);
+    }
+    const float sdl_w = warp_sum_f(acc_dlogit);
+    if (lane == 0) sf[F_RED + 64 + warp] = sdl_w;
+  }
+  __syncthreads();
+  if (!first) {
+    // folded semantic tail: logit = head_w . (W1 z1 + b1) + head_b, with v = sum dlogit * z1, s = sum dlogit
+    const float* v = sf + F_RED;
+    float sdl = 0.f;
+    for (int w = 0; w < kT / 32; ++w) sdl += sf[F_RED + 64 + w];
+    if (tid == 0) atomicAdd(G.head_b, sdl);
+    if (tid < H) {
+      const int j = tid;
+      const float hw = __ldg(P.head_w + j);
+      atomicAdd(G.sem_b[1] + j, hw * sdl);
+      float acc = __ldg(P.sem_b[1] + j) * sdl;
+      for (int k = 0; k < H; ++k) acc = fmaf(__ldg(P.sem_w[1] + j * H + k), v[k], acc);
+      atomicAdd(G.head_w + j, acc);
+    }
+    for (int e = tid; e < H * H; e += kT) {
+      const int j = e / H, k = e % H;
+      atomicAdd(G.sem_w[1] + e, __ldg(P.head_w + j) * v[k]);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(s_tmem_base, 512);
+}
+
+}  // namespace
+
+bool tc_backward_supported(Family fam, const KField& F, const KRays& Rr, const KFieldBwd& B) {
+  (void)Rr;
+  return fam == kFamilySmall && B.stash_encoding != nullptr && B.sample_rgb != nullptr && !F.pass_semantic_gradients &&
+         (F.appearance_mode == FNR_APP_PER_CAMERA || F.appearance_mode == FNR_APP_ZEROS);
+}
+
+int launch_tc_field_backward(Family fam, const KField& F, const KParams& P, const KParams& G, const KRays& Rr, const KFieldBwd& B,
+                             cudaStream_t st) {
+  if (!tc_backward_supported(fam, F, Rr, B)) {
+    set_error("tcgen05 backward kernel does not support this configuration");
+    return FNR_ERR_UNSUPPORTED;
+  }
+  const long long N = (long long)Rr.R * Rr.S;
+  if (N == 0) return FNR_OK;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_field_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tc_field_backward_kernel)");
+    configured = true;
+  }
+  BwdArgs a;
+  a.F = F;
+  a.P = P;
+  a.G = G;
+  a.Rr = Rr;
+  a.point_grads = B.point_grads;
+  a.stash_encoding = B.stash_encoding;
+  a.sample_rgb = B.sample_rgb;
+  const long long tiles = (N + kT - 1) / kT;
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  tc_field_backward_kernel<<<grid, kT, kSmem, st>>>(a);
+  return check_cuda(cudaGetLastError(), "tc_field_backward_kernel");
+}
+
+}  // namespace fnr

@@ -130,6 +130,12 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Instruction descriptor with explicit operand formats (0 = F16, 1 = BF16) and majors (1 = MN-major).
+__host__ __device__ constexpr uint32_t idesc_f32acc(int M, int N, int a_fmt, int b_fmt, int a_mn = 0, int b_mn = 0) {
+  return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // ---- bf16 hi/lo split ------------------------------------------------------------------------
 // x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits, full fp32 exponent range.
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -138,6 +144,26 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 __device__ __forceinline__ void split_bf16(float x, float& hi, float& lo) {
   hi = __bfloat162float(__float2bfloat16_rn(x));
+  lo = x - hi;
+}
+
+// ---- fp16 hi/lo split -------------------------------------------------------------------------
+// x ~= hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 mantissa bits.  Conversions saturate to the
+// finite fp16 range (|x| <= 65504); values below the fp16 subnormal floor lose only absolute 3e-8.
+__device__ __forceinline__ float f16_round_sat(float x) {
+  uint16_t h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  float y;
+  asm("cvt.f32.f16 %0, %1;" : "=f"(y) : "h"(h));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {  // a -> low half, b -> high half
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ void split_f16(float x, float& hi, float& lo) {
+  hi = f16_round_sat(x);
   lo = x - hi;
 }
 

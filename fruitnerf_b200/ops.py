@@ -189,7 +189,7 @@ class _Render(torch.autograd.Function):
             g_sd, g_srgb, g_ssem = g
             g_rgb = g_acc = g_sem = g_w = None
         gs = [None if t is None else _f32c(t) for t in (g_rgb, g_acc, g_sem, g_w, g_sd, g_srgb, g_ssem)]
-        desc = shape.desc(mode["position_mode"], mode["appearance_mode"], L.FNR_IMPL_SIMT)
+        desc = shape.desc(mode["position_mode"], mode["appearance_mode"], mode.get("bwd_impl", mode.get("impl", L.FNR_IMPL_AUTO)))
         pstruct = _params_struct(shape, params)
         flat, views = flat_zero_grads(params)
         gstruct = _params_struct(shape, views)

@@ -95,16 +95,17 @@ def field_forward(
         if cam.dim() == 1:
             cam = cam[:, None].expand(R, S)
         cam_flat = cam.reshape(-1)
-    dens, rgbs, sems, geos, encs = [], [], [], [], []
+    dens, rgbs, sems, geos, encs, margins = [], [], [], [], [], []
     N = pos_flat.shape[0]
     for a in range(0, N, chunk):
         b = min(N, a + chunk)
         enc = ns.hash_encode(pos_flat[a:b], table, scal, spec.log2_hashmap_size)
-        h = ns.mlp_forward(enc, bw, bb)
+        pre: list = []
+        h = ns.mlp_forward(enc, bw, bb, preacts=pre)
         d_before, geo = torch.split(h, [1, G], dim=-1)
         dens.append(ns.trunc_exp(d_before))
         sem_in = geo if spec.pass_semantic_gradients else geo.detach()
-        x = ns.mlp_forward(sem_in, sw, sb)
+        x = ns.mlp_forward(sem_in, sw, sb, preacts=pre)
         sems.append(torch.nn.functional.linear(x, params["field_head_semantics.net.weight"], params["field_head_semantics.net.bias"]))
         sh = ns.sh_degree4(dirs_flat[a:b])
         if appearance == "train":
@@ -115,7 +116,10 @@ def field_forward(
             app = torch.zeros((b - a, spec.appearance_embedding_dim))
         else:
             raise ValueError(appearance)
-        rgbs.append(ns.mlp_forward(torch.cat([sh, geo, app], dim=-1), cw, cb, out_activation="sigmoid"))
+        rgbs.append(ns.mlp_forward(torch.cat([sh, geo, app], dim=-1), cw, cb, out_activation="sigmoid", preacts=pre))
+        # ReLU margin of each point: min |pre-activation| / rms(layer), over every hidden unit (test hook: the
+        # gradient of a sample is only well-defined up to the mask of units this close to zero)
+        margins.append(torch.stack([(t.abs() / t.pow(2).mean().sqrt().clamp_min(1e-20)).amin(dim=-1) for t in pre], dim=-1).amin(dim=-1))
         geos.append(geo)
         encs.append(enc)
     density = torch.cat(dens).view(R, S, 1) * selector[..., None]
@@ -127,6 +131,7 @@ def field_forward(
         "encoding": torch.cat(encs).view(R, S, -1),
         "positions": pos,
         "selector": selector,
+        "relu_margin": torch.cat(margins).view(R, S),
     }
 
 

@@ -87,12 +87,16 @@ def hash_encode(p: Tensor, table: Tensor, scalings: Tensor, log2_hashmap_size: i
 # --------------------------------------------------------------------------------------
 # MLP / heads / activations     (fruit_field.py:132-166; components/field_heads.py:29-40)
 # --------------------------------------------------------------------------------------
-def mlp_forward(x: Tensor, weights: Sequence[Tensor], biases: Sequence[Tensor], out_activation: Optional[str] = None) -> Tensor:
-    """[NS] MLP.pytorch_fwd without skip connections: Linear(+bias) layers, ReLU between."""
+def mlp_forward(x: Tensor, weights: Sequence[Tensor], biases: Sequence[Tensor], out_activation: Optional[str] = None,
+                preacts: Optional[List[Tensor]] = None) -> Tensor:
+    """[NS] MLP.pytorch_fwd without skip connections: Linear(+bias) layers, ReLU between.
+    ``preacts`` (test hook) collects the detached ReLU inputs of the hidden layers."""
     n = len(weights)
     for i, (w, b) in enumerate(zip(weights, biases)):
         x = torch.nn.functional.linear(x, w, b)
         if i < n - 1:
+            if preacts is not None:
+                preacts.append(x.detach())
             x = torch.relu(x)
     if out_activation == "sigmoid":
         x = torch.sigmoid(x)

@@ -152,24 +152,45 @@ def test_render_eval_clamp_and_composite_edge_cases(native_lib, cuda_device):
     assert float(out["rgb"].min()) >= 0.0 and float(out["rgb"].max()) <= 1.0
 
 
-@pytest.mark.parametrize("name", ["small", "big"])
-def test_backward_matches_oracle_autograd(native_lib, cuda_device, name):
+RELU_MARGIN = 1e-4  # samples with a hidden pre-activation within 1e-4 (relative to the layer rms) of zero
+
+
+def _safe_ray_weights(f, R):
+    """1 for rays whose samples all keep a ReLU margin, else 0.  d relu(x)/dx at x ~ 0 depends on the
+    last bits of x: the tensor-core path computes pre-activations to ~2^-16 (bf16 hi/lo operands), the
+    oracle to ~2^-24, so masks may legitimately differ there and the sample's gradient changes
+    discretely.  Such rays get zero loss weight (on both sides), everything else is compared exactly."""
+    ok = (f["relu_margin"] > RELU_MARGIN).all(dim=1).float()
+    assert ok.sum() >= 8, f"only {int(ok.sum())} of {R} rays keep a ReLU margin; enlarge the batch"
+    return ok
+
+
+@pytest.mark.parametrize("impl", [L.FNR_IMPL_SIMT, L.FNR_IMPL_AUTO], ids=["simt", "auto"])
+@pytest.mark.parametrize("name,R,S", [("small", 128, 48), ("big", 128, 48), ("small", 111, 50)])
+def test_backward_matches_oracle_autograd(native_lib, cuda_device, name, R, S, impl):
+    """auto = fused tcgen05 forward + tensor-core backward where the shape is covered (small family),
+    simt kernels otherwise; 111 x 50 = 5550 points exercises a ragged last tile and warps that span rays."""
     sd, spec = make_state(name, log2T=15)  # small table keeps the oracle's dense grad comparison cheap
     field = make_field(name, sd, spec, cuda_device).train()
-    R, S = 64, 48
     o, d, s, e, cam = _rays(R, S, salt=5, far=3.0)
     img, mask = syn.targets(R)
-    out = _render_gpu(field, o, d, s, e, cam, L.FNR_IMPL_SIMT)
-    loss = torch.nn.functional.mse_loss(img.cuda(), out["rgb"]) + torch.nn.functional.binary_cross_entropy_with_logits(
-        out["semantics"][:, None], mask.cuda())
-    loss.backward()
 
     sd_ref = {k: v.clone().requires_grad_(v.is_floating_point() and k != "aabb") for k, v in sd.items()}
     f = _oracle_field(sd_ref, spec, o, d, s, e, cam, True, "train")
     ref = fr.render(f, s[..., None], e[..., None], training=True)
-    ld = fr.loss_dict(ref, img, mask)
-    (ld["rgb_loss"] + ld["semantics_loss"]).backward()
-    assert_rel(loss.detach(), (ld["rgb_loss"] + ld["semantics_loss"]).detach(), what="loss")
+    wr = _safe_ray_weights(f, R)[:, None]
+    bce = torch.nn.functional.binary_cross_entropy_with_logits
+
+    def loss_of(rgb, sem, w, image, m):
+        return (w * (image - rgb) ** 2).sum() / (3 * R) + (w * bce(sem, m, reduction="none")).sum() / R
+
+    loss_ref = loss_of(ref["rgb"], ref["semantics"], wr, img, mask)
+    loss_ref.backward()
+
+    out = _render_gpu(field, o, d, s, e, cam, impl)
+    loss = loss_of(out["rgb"], out["semantics"][:, None], wr.cuda(), img.cuda(), mask.cuda())
+    loss.backward()
+    assert_rel(loss.detach(), loss_ref.detach(), what="loss")
 
     named = dict(field.named_parameters())
     for key, ref_t in sd_ref.items():
@@ -178,24 +199,29 @@ def test_backward_matches_oracle_autograd(native_lib, cuda_device, name):
         g_ref = ref_t.grad if ref_t.grad is not None else torch.zeros_like(ref_t)
         g = named[key].grad
         assert g is not None, key
-        # gradient tolerance: 1e-3 of the tensor's scale (sums over thousands of samples, fp32 atomics)
+        # gradient tolerance: 2e-3 of max(|g|, 25% of the tensor's scale) (sums over thousands of samples, fp32 atomics)
         assert_rel(g, g_ref, rel=2e-3, floor=0.25, what=f"grad {key}")
 
 
-def test_field_only_backward(native_lib, cuda_device):
+@pytest.mark.parametrize("impl", [L.FNR_IMPL_SIMT, L.FNR_IMPL_AUTO], ids=["simt", "auto"])
+def test_field_only_backward(native_lib, cuda_device, impl):
     """FruitField.forward users: gradients w.r.t. per-sample outputs flow to the parameters."""
     sd, spec = make_state("small", log2T=15)
     field = make_field("small", sd, spec, cuda_device).train()
+    field.kernel_impl = impl
     R, S = 32, 16
     o, d, s, e, cam = _rays(R, S, salt=9, far=2.0)
     rs = RaySamples(frustums=Frustums(o[:, None, :].expand(R, S, 3).cuda(), d[:, None, :].expand(R, S, 3).cuda(),
                                       s[..., None].cuda(), e[..., None].cuda()),
                     camera_indices=cam[:, None, None].expand(R, S, 1).cuda())
-    out = field(rs)
-    (out[FieldHeadNames.RGB].sum() + 0.1 * out[FieldHeadNames.DENSITY].sum() + out[FieldHeadNames.SEMANTICS].pow(2).sum()).backward()
     sd_ref = {k: v.clone().requires_grad_(v.is_floating_point() and k != "aabb") for k, v in sd.items()}
     f = _oracle_field(sd_ref, spec, o, d, s, e, cam, True, "train")
-    (f["rgb"].sum() + 0.1 * f["density"].sum() + f["semantics"].pow(2).sum()).backward()
+    w = (f["relu_margin"] > RELU_MARGIN).float()[..., None]  # per-sample weights (see _safe_ray_weights)
+    (w * f["rgb"]).sum().add(0.1 * (w * f["density"]).sum()).add((w * f["semantics"].pow(2)).sum()).backward()
+    out = field(rs)
+    wg = w.cuda()
+    ((wg * out[FieldHeadNames.RGB]).sum() + 0.1 * (wg * out[FieldHeadNames.DENSITY]).sum()
+     + (wg * out[FieldHeadNames.SEMANTICS].pow(2)).sum()).backward()
     named = dict(field.named_parameters())
     for key in ("mlp_base_grid.hash_table", "mlp_base_mlp.layers.0.weight", "mlp_semantics.layers.1.weight",
                 "field_head_semantics.net.bias", "mlp_head.layers.0.weight", "embedding_appearance.embedding.weight"):

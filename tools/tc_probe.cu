@@ -8,6 +8,8 @@
 //             [N rows][K cols] tile a forward GEMM uses (no transposed copy)
 //     mode 4: "dW" form: D[64,K] = A[128,64]^T * X[128,K], both operands MN-major views of canonical
 //             row-per-point tiles (reduction over the 128 points), M=64 accumulator layout
+//     mode 5: SS, A = bf16, B = fp16 in the same MMA (mixed operand formats)
+//     mode 6: SS, fp16 hi/lo split on both operands (3 MMAs per K step) vs exact fp32 product
 //     swap 1: exchange the LBO / SBO fields of the descriptors (layout-convention check)
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tools/bin/tc_probe tools/tc_probe.cu
 #include <cuda_runtime.h>
@@ -51,14 +53,22 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ A,
     mbar_fence_init();
   }
   // stage A (thread t = row t) and B (rows strided over threads) in the canonical layout
+  const bool a_f16 = mode == 6, b_f16 = mode == 5 || mode == 6;
   for (int j = 0; j < chunks; ++j) {
     uint32_t hi[4], lo[4];
     for (int q = 0; q < 4; ++q) {
       float a0 = A[t * K + j * 8 + 2 * q], a1 = A[t * K + j * 8 + 2 * q + 1], h0, l0, h1, l1;
-      split_bf16(a0, h0, l0);
-      split_bf16(a1, h1, l1);
-      hi[q] = pack_bf16x2(h0, h1);
-      lo[q] = pack_bf16x2(l0, l1);
+      if (a_f16) {
+        split_f16(a0, h0, l0);
+        split_f16(a1, h1, l1);
+        hi[q] = pack_f16x2(h0, h1);
+        lo[q] = pack_f16x2(l0, l1);
+      } else {
+        split_bf16(a0, h0, l0);
+        split_bf16(a1, h1, l1);
+        hi[q] = pack_bf16x2(h0, h1);
+        lo[q] = pack_bf16x2(l0, l1);
+      }
     }
     *reinterpret_cast<uint4*>(sA_hi + j * 128 * 16 + t * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(sA_lo + j * 128 * 16 + t * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -68,10 +78,17 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ A,
       uint32_t hi[4], lo[4];
       for (int q = 0; q < 4; ++q) {
         float b0 = B[n * K + j * 8 + 2 * q], b1 = B[n * K + j * 8 + 2 * q + 1], h0, l0, h1, l1;
-        split_bf16(b0, h0, l0);
-        split_bf16(b1, h1, l1);
-        hi[q] = pack_bf16x2(h0, h1);
-        lo[q] = pack_bf16x2(l0, l1);
+        if (b_f16) {
+          split_f16(b0, h0, l0);
+          split_f16(b1, h1, l1);
+          hi[q] = pack_f16x2(h0, h1);
+          lo[q] = pack_f16x2(l0, l1);
+        } else {
+          split_bf16(b0, h0, l0);
+          split_bf16(b1, h1, l1);
+          hi[q] = pack_bf16x2(h0, h1);
+          lo[q] = pack_bf16x2(l0, l1);
+        }
       }
       *reinterpret_cast<uint4*>(sB_hi + j * N * 16 + n * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       *reinterpret_cast<uint4*>(sB_lo + j * N * 16 + n * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -103,7 +120,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ A,
   }
 
   if (t == 0) {
-    const uint32_t idesc = idesc_bf16_f32(128, N);
+    const uint32_t idesc = idesc_f32acc(128, N, a_f16 ? 0 : 1, b_f16 ? 0 : 1);
     const uint32_t a_lbo = swap ? 128 : 128 * 16, a_sbo = swap ? 128 * 16 : 128;
     const uint32_t b_lbo = swap ? 128 : N * 16, b_sbo = swap ? N * 16 : 128;
     bool acc = false;
@@ -116,7 +133,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ A,
         mma_ts(d_tmem, a_tmem + ks * 8, bh, idesc, acc);
       } else {
         mma_ss(d_tmem, ah, bh, idesc, acc);
-        if (mode == 2) {
+        if (mode == 2 || mode == 6) {
           mma_ss(d_tmem, al, bh, idesc, true);
           mma_ss(d_tmem, ah, bl, idesc, true);
         }
@@ -149,6 +166,9 @@ static float bf16_round(float x) {
   memcpy(&y, &r, 4);
   return y;
 }
+
+#include <cuda_fp16.h>
+static float f16_round_host(float x) { return __half2float(__float2half_rn(x)); }
 
 __host__ __device__ constexpr uint32_t idesc_major(int M, int N, int a_mn, int b_mn) {
   return idesc_bf16_f32(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
@@ -315,14 +335,14 @@ int main(int argc, char** argv) {
     for (int n = 0; n < N; ++n) {
       double ref = 0;
       for (int k = 0; k < K; ++k) {
-        const double a = mode == 2 ? A[m * K + k] : bf16_round(A[m * K + k]);
-        const double b = mode == 2 ? B[n * K + k] : bf16_round(B[n * K + k]);
+        const double a = (mode == 2 || mode == 6) ? A[m * K + k] : bf16_round(A[m * K + k]);
+        const double b = (mode == 2 || mode == 6) ? B[n * K + k] : (mode == 5 ? f16_round_host(B[n * K + k]) : bf16_round(B[n * K + k]));
         ref += a * b;
       }
       max_err = fmax(max_err, fabs(ref - D[m * N + n]));
       max_ref = fmax(max_ref, fabs(ref));
     }
-  const double tol = mode == 2 ? 2e-4 : 2e-5;
+  const double tol = mode == 2 ? 2e-4 : (mode == 6 ? 2e-6 : 2e-5);
   printf("PROBE mode=%d N=%d K=%d swap=%d : timeout=%d max_err=%.3e max_ref=%.3e rel=%.3e %s\n", mode, N, K, swap, timeout, max_err,
          max_ref, max_err / max_ref, (!timeout && max_err / max_ref < tol) ? "PASS" : "FAIL");
   return 0;
