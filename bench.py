@@ -115,7 +115,7 @@ def build_field(variant: str, device, table_scale: float = 1e-1):
 
 
 def step_fn(field, batch, world, impl_id):
-    """One step through the public op (the call FruitModel.get_outputs makes)."""
+    """One eager step through the public op (the call FruitModel.get_outputs makes) -- used by tools/."""
     from fruitnerf_b200 import ops
 
     o, d, s, e, cam, img, mask = batch
@@ -130,6 +130,7 @@ def run_ours(args):
     from fruitnerf_b200 import _lib as L
     from fruitnerf_b200 import ops
     from fruitnerf_b200 import synthetic as syn
+    from fruitnerf_b200.engine import GraphedTrainStep
 
     L.load()
     if not torch.cuda.is_available():
@@ -137,9 +138,8 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -148,38 +148,29 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     impl_id = {"auto": L.FNR_IMPL_AUTO, "simt": L.FNR_IMPL_SIMT, "tcgen05": L.FNR_IMPL_TCGEN05}[args.kernel]
     field = build_field(args.variant, dev)
-    params = field.kernel_params()
     N_pts = R_RAYS * S_SAMPLES
 
     # per-rank batch (weak scaling: each rank draws its own 4096 rays, fruit_pipeline.py:97-99)
     o, d, s, e, cam = syn.ray_batch(R_RAYS, S_SAMPLES, salt=rank, num_images=NUM_IMAGES)
     img, mask = syn.targets(R_RAYS, salt=rank)
     host = [t.pin_memory() for t in (o, d, s, e, cam.to(torch.int32), img, mask)]
-    batch = [t.to(dev) for t in host]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
-    def one_step(b, timing=None):
-        for p in params:
-            p.grad = None
-        if timing:
-            timing[0].record()
-        out, loss = step_fn(field, b, world, impl_id)
-        if timing:
-            timing[1].record()
-        loss.backward()
-        flat = ops._Render.last_flat_grad
-        if timing:
-            timing[2].record()
+    # the public training-step API: render fwd + loss + bwd captured in one CUDA graph
+    step = GraphedTrainStep(field, R_RAYS, S_SAMPLES, impl=impl_id, use_graph=not args.no_graph)
+    h2d = step.load_batch(*host)
+    step.capture(warmup=max(args.warmup, 3))
+
+    def one_step():
+        loss = step()
         if world > 1:
             import torch.distributed as dist
 
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-        if timing:
-            timing[3].record()
+            dist.all_reduce(step.flat_grad, op=dist.ReduceOp.AVG)  # the reference's DDP exchange
         return loss
 
     for _ in range(max(args.warmup, 3)):
-        one_step(batch)
+        one_step()
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local) if (rank == 0 and not args.no_clocks) else None
@@ -190,20 +181,20 @@ def run_ours(args):
     torch.cuda.synchronize()
     if sampler:
         sampler.start()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     for i in range(args.steps):
         if not args.no_flush:
             flush.fill_(float(i))  # evict the table / weights from L2 between timed steps
-        one_step(batch, evs[i])
+        evs[i][0].record()
+        one_step()
+        evs[i][1].record()
     torch.cuda.synchronize()
     if world > 1:
         import torch.distributed as dist
 
         dist.barrier()
     clocks = sampler.stop() if sampler else None
-    step_ms = [ev[0].elapsed_time(ev[3]) for ev in evs]
-    fwd_ms = [ev[0].elapsed_time(ev[1]) for ev in evs]
-    bwd_ms = [ev[1].elapsed_time(ev[2]) for ev in evs]
+    step_ms = [ev[0].elapsed_time(ev[1]) for ev in evs]
     total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
     if world > 1:
         import torch.distributed as dist
@@ -211,15 +202,42 @@ def run_ours(args):
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms)
 
-    # end-to-end through the public op with HOST buffers: H2D of the step's rays/targets and a
-    # D2H read of the loss inside the timed region
-    e2e_steps = args.steps
+    # forward kernel alone (training forward: writes the encoding stash), for the roofline of the fused forward
+    st = step.static
+    fwd_graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+
+    def fwd_only():
+        return ops.render(field.kernel_shape(), field.kernel_params(), st["origins"], st["directions"], st["starts"], st["ends"],
+                          st["camera_indices"], field.position_mode(), field.appearance_mode(), impl=impl_id)
+
+    with torch.cuda.stream(side):
+        fwd_only()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(fwd_graph):
+        fwd_out = fwd_only()
+    fev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+    for i in range(args.steps):
+        if not args.no_flush:
+            flush.fill_(float(i))
+        fev[i][0].record()
+        fwd_graph.replay()
+        fev[i][1].record()
+    torch.cuda.synchronize()
+    fwd_ms = [ev[0].elapsed_time(ev[1]) for ev in fev]
+    del fwd_out
+
+    # end-to-end through the public API with HOST buffers: per step H2D of the rays/targets from pinned
+    # memory, one graph replay, D2H read of the loss -- all inside the timed region
+    e2e_steps = max(args.steps, 20)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        b = [t.to(dev, non_blocking=True) for t in host]
-        loss = one_step(b)
-        _ = float(loss.detach())  # D2H
+        step.load_batch(*host)
+        loss = one_step()
+        _ = float(loss)  # D2H + sync
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
@@ -227,17 +245,18 @@ def run_ours(args):
 
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s)
-    h2d = sum(t.numel() * t.element_size() for t in host)
 
     if rank != 0:
         return
     peak, peak_src = _peaks()
-    mean_fwd, mean_bwd = sum(fwd_ms) / len(fwd_ms), sum(bwd_ms) / len(bwd_ms)
+    mean_step = total_ms / args.steps
+    mean_fwd = sum(fwd_ms) / len(fwd_ms)
+    mean_bwd = max(mean_step - mean_fwd, 1e-6)
+    fwd_bytes = N_pts * HASH_BYTES_PER_POINT_FWD
+    bwd_bytes = N_pts * HASH_BYTES_PER_POINT_BWD
+    fwd_ach = fwd_bytes / (mean_fwd * 1e-3) / 1e9
+    bwd_ach = bwd_bytes / (mean_bwd * 1e-3) / 1e9
     dominant_is_bwd = mean_bwd >= mean_fwd
-    dom_ms = mean_bwd if dominant_is_bwd else mean_fwd
-    dom_bytes = N_pts * (HASH_BYTES_PER_POINT_BWD if dominant_is_bwd else HASH_BYTES_PER_POINT_FWD)
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    fwd_achieved = N_pts * HASH_BYTES_PER_POINT_FWD / (mean_fwd * 1e-3) / 1e9
     line = {
         "metric": "rays/sec (4096 rays x 192 samples) fused fwd+bwd",
         "value": world * R_RAYS * args.steps / (total_ms * 1e-3),
@@ -245,7 +264,7 @@ def run_ours(args):
         "n_gpus": world,
         "steps": args.steps,
         "warmup": max(args.warmup, 3),
-        "ms_per_step": total_ms / args.steps,
+        "ms_per_step": mean_step,
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
@@ -258,6 +277,7 @@ def run_ours(args):
             "kernel": args.kernel,
             "rays_per_gpu": R_RAYS,
             "samples_per_ray": S_SAMPLES,
+            "execution": "eager" if args.no_graph else "one CUDA graph per step (fruitnerf_b200.engine.GraphedTrainStep)",
             "l2": "flushed between timed steps (256 MiB fill); per-step CUDA-event durations summed",
             "parallelism": f"dp{world}",
         },
@@ -265,21 +285,25 @@ def run_ours(args):
         "bwd_ms": mean_bwd,
         "fwd_rays_per_s": R_RAYS / (mean_fwd * 1e-3),
         "roofline": {
-            "kernel": "render backward (simt_field_backward_kernel + composite bwd)" if dominant_is_bwd else "render forward",
+            "kernel": ("render backward (tc_field_backward_kernel + composite backward + loss)" if dominant_is_bwd
+                       else "fused render forward (tc_render_forward_kernel)"),
             "bound": "hbm",
-            "achieved": achieved,
+            "achieved": bwd_ach if dominant_is_bwd else fwd_ach,
             "peak": peak,
             "unit": "GB/s",
-            "frac": achieved / peak,
+            "frac": (bwd_ach if dominant_is_bwd else fwd_ach) / peak,
             "traffic": None,
             "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": dom_bytes,
-            "launch_ms": dom_ms,
+            "algorithmic_bytes_per_launch": bwd_bytes if dominant_is_bwd else fwd_bytes,
+            "launch_ms": mean_bwd if dominant_is_bwd else mean_fwd,
         },
-        "roofline_forward": {"bound": "hbm", "achieved": fwd_achieved, "peak": peak, "unit": "GB/s", "frac": fwd_achieved / peak,
-                             "launch_ms": mean_fwd, "algorithmic_bytes_per_launch": N_pts * HASH_BYTES_PER_POINT_FWD},
-        "e2e": {"value": world * R_RAYS * e2e_steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-        "gpu_launches": 4 * args.steps,
+        "roofline_forward": {"kernel": "tc_render_forward_kernel", "bound": "hbm", "achieved": fwd_ach, "peak": peak, "unit": "GB/s",
+                             "frac": fwd_ach / peak, "launch_ms": mean_fwd, "algorithmic_bytes_per_launch": fwd_bytes},
+        "roofline_step": {"bound": "hbm", "achieved": (fwd_bytes + bwd_bytes) / (mean_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": (fwd_bytes + bwd_bytes) / (mean_step * 1e-3) / 1e9 / peak},
+        "e2e": {"value": world * R_RAYS * e2e_steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "steps": e2e_steps},
+        "gpu_launches": 3 * args.steps,
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu:
@@ -362,6 +386,7 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--cpu-rays", type=int, default=2048)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="diagnostic: eager step instead of the CUDA-graph step")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic: skip the L2 flush between timed steps")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample nvidia-smi during the timed region")
     args = ap.parse_args()

@@ -1,0 +1,108 @@
+"""CUDA-graph execution of the training hot step.
+
+One FruitNeRF training iteration on the hot path is a handful of kernels that together run for ~1-2 ms
+on a B200; enqueueing them op by op from Python costs more than executing them.  ``GraphedTrainStep``
+captures the body of ``FruitPipeline.get_train_loss_dict`` + ``backward`` for a fixed batch shape --
+fused render forward, MSE / BCE-with-logits loss (fruit_nerf/fruit_nerf.py:359-366), tensor-core
+backward into the flat gradient buffer -- into ONE CUDA graph and replays it per step.  Inputs live in
+static device buffers that ``load_batch`` refreshes (asynchronous H2D copies from pinned memory).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+from . import ops
+
+
+def default_loss(outputs: Dict[str, Tensor], image: Tensor, fruit_mask: Tensor, semantic_loss_weight: float = 1.0) -> Tensor:
+    """rgb MSE + semantic BCE-with-logits (get_loss_dict without the interlevel term)."""
+    return torch.nn.functional.mse_loss(image, outputs["rgb"]) + semantic_loss_weight * torch.nn.functional.binary_cross_entropy_with_logits(
+        outputs["semantics"][:, None], fruit_mask)
+
+
+class GraphedTrainStep:
+    def __init__(self, field, num_rays: int, num_samples: int, impl: int = L.FNR_IMPL_AUTO, semantic_loss_weight: float = 1.0,
+                 use_graph: bool = True):
+        self.field = field
+        self.impl = impl
+        self.semantic_loss_weight = semantic_loss_weight
+        dev = next(field.parameters()).device
+        self.device = dev
+        R, S = num_rays, num_samples
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.static = {
+            "origins": torch.zeros(R, 3, **f32),
+            "directions": torch.zeros(R, 3, **f32),
+            "starts": torch.zeros(R, S, **f32),
+            "ends": torch.ones(R, S, **f32),
+            "camera_indices": torch.zeros(R, dtype=torch.int32, device=dev),
+            "image": torch.zeros(R, 3, **f32),
+            "fruit_mask": torch.zeros(R, 1, **f32),
+        }
+        self.params = field.kernel_params()
+        self.loss: Optional[Tensor] = None
+        self.outputs: Optional[Dict[str, Tensor]] = None
+        self.flat_grad: Optional[Tensor] = None
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.use_graph = use_graph
+        self._captured = False
+
+    # ---- inputs -----------------------------------------------------------------------------------
+    def load_batch(self, origins, directions, starts, ends, camera_indices, image, fruit_mask, non_blocking: bool = True) -> int:
+        """Copy one batch (host pinned or device tensors) into the static buffers; returns bytes copied."""
+        src = dict(origins=origins, directions=directions, starts=starts, ends=ends, camera_indices=camera_indices, image=image,
+                   fruit_mask=fruit_mask)
+        n = 0
+        for k, t in src.items():
+            dst = self.static[k]
+            if t.dtype != dst.dtype:
+                t = t.to(dst.dtype)
+            dst.copy_(t.reshape(dst.shape), non_blocking=non_blocking)
+            n += dst.numel() * dst.element_size()
+        return n
+
+    # ---- the step ---------------------------------------------------------------------------------
+    def _eager(self) -> Tensor:
+        f, st = self.field, self.static
+        for p in self.params:
+            p.grad = None
+        out = ops.render(f.kernel_shape(), self.params, st["origins"], st["directions"], st["starts"], st["ends"], st["camera_indices"],
+                         f.position_mode(), f.appearance_mode(), impl=self.impl)
+        loss = default_loss(out, st["image"], st["fruit_mask"], self.semantic_loss_weight)
+        loss.backward()
+        self.outputs, self.loss = out, loss.detach()
+        self.flat_grad = ops._Render.last_flat_grad
+        return self.loss
+
+    def capture(self, warmup: int = 3) -> None:
+        if not self.use_graph:
+            self._captured = True
+            return
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        for p in self.params:
+            p.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._eager()
+        self._captured = True
+
+    def __call__(self) -> Tensor:
+        """Run one step on the current static batch; returns the (static) scalar loss tensor.  Parameter
+        ``.grad`` tensors are views of ``flat_grad`` (one buffer for the multi-GPU all-reduce)."""
+        if not self._captured:
+            self.capture()
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._eager()
+        return self.loss
