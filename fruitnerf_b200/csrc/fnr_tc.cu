@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
   const uint32_t wBase = smem_u32(smem);
   uint64_t* bar = &s_bar[slot];
   uint32_t phase = 0;
-  const bool issuer = (warp & 3) == 0 && lane == 0;
+  const bool issue_warp = (warp & 3) == 0;
   const int bar_id = 1 + slot;
 
   const int S = a.Rr.S, R = a.Rr.R;
@@ -215,10 +215,13 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
       fence_async_smem();
       fence_before_sync();
       named_bar_sync(bar_id, 128);
-      if (issuer) {
-        fence_after_sync();
-        issue_gemm<K_BASE0, N_BASE0>(tmem_slot + C_R0, aQ, wBase + OFF_W_BASE0);
-        mma_commit(bar);
+      if (issue_warp) {
+        if (elect_one_sync()) {
+          fence_after_sync();
+          issue_gemm<K_BASE0, N_BASE0>(tmem_slot + C_R0, aQ, wBase + OFF_W_BASE0);
+          mma_commit(bar);
+        }
+        __syncwarp();
       }
 
       // ---- epilogue 1: h1 = relu(base0 + b) -> P ; sh / appearance part of the colour input -> Q later
@@ -261,10 +264,13 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
       fence_async_smem();
       fence_before_sync();
       named_bar_sync(bar_id, 128);
-      if (issuer) {
-        fence_after_sync();
-        issue_gemm<K_BASE1, N_BASE1>(tmem_slot + C_R1, aP, wBase + OFF_W_BASE1);
-        mma_commit(bar);
+      if (issue_warp) {
+        if (elect_one_sync()) {
+          fence_after_sync();
+          issue_gemm<K_BASE1, N_BASE1>(tmem_slot + C_R1, aP, wBase + OFF_W_BASE1);
+          mma_commit(bar);
+        }
+        __syncwarp();
       }
       // colour-input chunks that do not depend on geo: [sh 0..15 | app 0..31] = chunks 0..5 of Q
       // (the encoding tile in Q is dead: its GEMM completed before epilogue 1 ran)
@@ -310,11 +316,14 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
       fence_async_smem();
       fence_before_sync();
       named_bar_sync(bar_id, 128);
-      if (issuer) {
-        fence_after_sync();
-        issue_gemm<K_SEM0, N_SEM0>(tmem_slot + C_R2, aS, wBase + OFF_W_SEM0);
-        issue_gemm<K_COL0, N_COL0>(tmem_slot + C_R0, aQ, wBase + OFF_W_COL0);
-        mma_commit(bar);
+      if (issue_warp) {
+        if (elect_one_sync()) {
+          fence_after_sync();
+          issue_gemm<K_SEM0, N_SEM0>(tmem_slot + C_R2, aS, wBase + OFF_W_SEM0);
+          issue_gemm<K_COL0, N_COL0>(tmem_slot + C_R0, aQ, wBase + OFF_W_COL0);
+          mma_commit(bar);
+        }
+        __syncwarp();
       }
 
       // ---- epilogue 3: z1 = relu(sem0 + b) -> P ; c1 = relu(col0 + b) -> Q -------------------------
@@ -344,11 +353,14 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
       fence_async_smem();
       fence_before_sync();
       named_bar_sync(bar_id, 128);
-      if (issuer) {
-        fence_after_sync();
-        issue_gemm<K_SEMH, N_SEMH>(tmem_slot + C_R1, aP, wBase + OFF_W_SEMH);
-        issue_gemm<K_COL1, N_COL1>(tmem_slot + C_R0, aQ, wBase + OFF_W_COL1);
-        mma_commit(bar);
+      if (issue_warp) {
+        if (elect_one_sync()) {
+          fence_after_sync();
+          issue_gemm<K_SEMH, N_SEMH>(tmem_slot + C_R1, aP, wBase + OFF_W_SEMH);
+          issue_gemm<K_COL1, N_COL1>(tmem_slot + C_R0, aQ, wBase + OFF_W_COL1);
+          mma_commit(bar);
+        }
+        __syncwarp();
       }
 
       // ---- epilogue 4: logit ; c2 = relu(col1 + b) -> P --------------------------------------------
@@ -378,10 +390,13 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
       fence_async_smem();
       fence_before_sync();
       named_bar_sync(bar_id, 128);
-      if (issuer) {
-        fence_after_sync();
-        issue_gemm<K_COL2, N_COL2>(tmem_slot + C_R1, aP, wBase + OFF_W_COL2);
-        mma_commit(bar);
+      if (issue_warp) {
+        if (elect_one_sync()) {
+          fence_after_sync();
+          issue_gemm<K_COL2, N_COL2>(tmem_slot + C_R1, aP, wBase + OFF_W_COL2);
+          mma_commit(bar);
+        }
+        __syncwarp();
       }
 
       // ---- epilogue 5: rgb = sigmoid(col2 + b) ; per-sample results to shared memory ---------------

@@ -11,11 +11,14 @@
 // backward clamps the exponent to [-15, 15]); upstream per-sample gradients come from the compositing
 // backward (simt_composite_backward_kernel).
 //
-// One persistent CTA of 128 threads per SM: thread r owns point r of the tile (TMEM lane r).  All operands
+// One persistent CTA of 256 threads per SM: the thread pair (r, r+128) owns point r of the tile (TMEM lane r);
+// the two threads split every 64-column epilogue and the 16 hash levels in halves (two warps may touch the
+// same TMEM lane quarter), which doubles the loads / TMEM reads in flight of the single MMA slot.  All operands
 // are bf16 hi/lo splits (3 MMAs per K-step, ~2^-16 per product); the K=16 "[geo | 1]" operand of the
 // semantic branch is chunks 6-7 of the colour-input tile, so no activation is stored twice.
 // Bias gradients come for free from constant-1 columns (padding columns of the geo / colour-input tiles,
 // a 128x16 ONES tile for the K-exact layers) or from per-thread running sums (3- and 16-wide layers).
+#include <cstdlib>
 #include "fnr_common.cuh"
 #include "fnr_kernels.h"
 #include "fnr_tc_common.cuh"
@@ -26,7 +29,7 @@ using namespace tcx;
 
 namespace {
 
-constexpr int kT = 128;  // threads per CTA
+constexpr int kT = 256;  // threads per CTA: 2 threads per point (column halves), 8 warps
 constexpr int GEO = 15, ENC = 32, H = 64, APP = 32, SHD = 16;
 
 // ---- shared-memory map (bytes) ------------------------------------------------------------------
@@ -89,9 +92,11 @@ __device__ __forceinline__ void issue_dx(uint32_t d_tmem, uint32_t a_hi, uint32_
 
 // ACC[FA=64, FB] (+)= A[128, 64]^T * B[128, FB]   (both row-per-point tiles read MN-major, K = 128 points).
 // a_lo / b_lo: shared addresses of the lo halves (0 = operand not split).
+__device__ int g_skip_dw;
 template <int FB>
 __device__ __forceinline__ void issue_dw(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, bool accumulate) {
   constexpr uint32_t idesc = idesc_mn(64, FB, 1, 1);
+  if (g_skip_dw) return;
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
     const uint64_t ah = smem_desc(a_hi + ks * 256, 128, 2048);
@@ -102,46 +107,50 @@ __device__ __forceinline__ void issue_dw(uint32_t d_tmem, uint32_t a_hi, uint32_
   }
 }
 
-// Read this thread's 64 accumulator columns (+ bias), optional ReLU.
-template <bool RELU>
-__device__ __forceinline__ void load_row64(uint32_t taddr, const float* bias, float (&v)[64]) {
-  uint32_t r0[32], r1[32];
-  tmem_ld32(taddr, r0);
-  tmem_ld32(taddr + 32, r1);
+// ---- column-split epilogues: the two threads (row, half=0/1) of a row each own 32 of the 64 columns ----
+// v = f(column n, accumulator value); stores chunks 4*half .. 4*half+3 of a K=64 hi/lo tile.
+template <class Fn>
+__device__ __forceinline__ void epi32(uint32_t taddr32, uint8_t* tile, int row, int half, Fn f) {
+  uint32_t r[4][8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) tmem_ld8(taddr32 + 8 * j, r[j]);
   tmem_ld_wait();
 #pragma unroll
-  for (int n = 0; n < 64; ++n) {
-    float x = __uint_as_float(n < 32 ? r0[n] : r1[n - 32]);
-    if (bias) x += bias[n];
-    v[n] = RELU ? fmaxf(x, 0.f) : x;
-  }
-}
-
-__device__ __forceinline__ void store_row64(uint8_t* tile, int row, const float (&v)[64]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 4; ++j) {
     float c[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) c[q] = v[8 * j + q];
-    store_chunk(tile, 128 * 64 * 2, row, j, c);
+    for (int q = 0; q < 8; ++q) c[q] = f(32 * half + 8 * j + q, __uint_as_float(r[j][q]));
+    store_chunk(tile, 128 * 64 * 2, row, 4 * half + j, c);
   }
 }
 
-// ReLU mask of a stored 64-wide tile row (hi half): bit n set iff activation n > 0.
-__device__ __forceinline__ unsigned long long relu_mask64(const uint8_t* tile_hi, int row) {
-  unsigned long long m = 0ull;
+// 8-bit ReLU mask of chunk j of a stored K=64 tile row (hi half): bit q set iff activation 8j+q > 0.
+__device__ __forceinline__ uint32_t relu_mask8(const uint8_t* tile_hi, int row, int j) {
+  const uint4 u = *reinterpret_cast<const uint4*>(tile_hi + j * 2048 + row * 16);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  uint32_t m = 0;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const uint4 u = *reinterpret_cast<const uint4*>(tile_hi + j * 2048 + row * 16);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      // bf16 > 0  <=>  non-zero magnitude and sign bit clear (activations are relu outputs: never negative)
-      if (w[q] & 0x7FFFu) m |= 1ull << (8 * j + 2 * q);
-      if (w[q] & 0x7FFF0000u) m |= 1ull << (8 * j + 2 * q + 1);
-    }
+  for (int q = 0; q < 4; ++q) {
+    if (w[q] & 0x7FFFu) m |= 1u << (2 * q);
+    if (w[q] & 0x7FFF0000u) m |= 1u << (2 * q + 1);
   }
   return m;
+}
+
+// dX epilogue: v = acc * relu'(stored activation of the same column) -> DY tile.
+__device__ __forceinline__ void epi32_masked(uint32_t taddr32, const uint8_t* act_tile, uint8_t* dst, int row, int half) {
+  uint32_t r[4][8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) tmem_ld8(taddr32 + 8 * j, r[j]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t m = relu_mask8(act_tile, row, 4 * half + j);
+    float c[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) c[q] = ((m >> q) & 1u) ? __uint_as_float(r[j][q]) : 0.f;
+    store_chunk(dst, 128 * 64 * 2, row, 4 * half + j, c);
+  }
 }
 
 struct BwdArgs {
@@ -152,6 +161,7 @@ struct BwdArgs {
   const float* point_grads;     // [N,5]  d_density, d_rgb[3], d_logit
   const float* stash_encoding;  // [N,32]
   const float* sample_rgb;      // [N,3]
+  int debug_flags;              // FNR_DEBUG_BWD env (bit 0: skip table scatter, bit 1: skip dW GEMMs) -- timing experiments only
 };
 
 __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_constant__ BwdArgs a) {
@@ -160,7 +170,8 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
   __shared__ uint32_t s_tmem_base;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = tid;
+  const int row = tid & 127;   // point (TMEM lane) of this thread
+  const int half = tid >> 7;   // which 32 of 64 accumulator columns / which 8 of 16 levels this thread owns
   const KParams& P = a.P;
   const KParams& G = a.G;
   const KField& F = a.F;
@@ -198,7 +209,7 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
     }
     sf[i] = v;
   }
-  {  // ONES tile: column 0 = 1 (bf16 0x3F80), everything else 0
+  if (half == 0) {  // ONES tile: column 0 = 1 (bf16 0x3F80), everything else 0
     uint8_t* ones = smem + OFF_ONES;
     *reinterpret_cast<uint4*>(ones + row * 16) = make_uint4(0x00003F80u, 0u, 0u, 0u);
     *reinterpret_cast<uint4*>(ones + 2048 + row * 16) = make_uint4(0u, 0u, 0u, 0u);
@@ -209,7 +220,7 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
   fence_after_sync();
 
   const uint32_t tb = s_tmem_base;
-  const uint32_t trow = tb + ((uint32_t)(warp * 32) << 16);
+  const uint32_t trow = tb + ((uint32_t)((warp & 3) * 32) << 16);
   uint8_t* tH = smem + OFF_H;
   uint8_t* tD16 = smem + OFF_D16;
   uint8_t* tCIN = smem + OFF_CIN;
@@ -217,40 +228,44 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
   uint8_t* tC1 = smem + OFF_C1;
   uint8_t* tDY = smem + OFF_DY;
   const uint32_t sb = smem_u32(smem);
-  const uint32_t aH = sb + OFF_H, aD16 = sb + OFF_D16, aCIN = sb + OFF_CIN, aA = sb + OFF_A, aC1 = sb + OFF_C1,
-                 aDY = sb + OFF_DY, aONES = sb + OFF_ONES;
+  const uint32_t aH = sb + OFF_H, aD16 = sb + OFF_D16, aCIN = sb + OFF_CIN, aA = sb + OFF_A, aC1 = sb + OFF_C1, aDY = sb + OFF_DY,
+                 aONES = sb + OFF_ONES;
   constexpr uint32_t LO64 = 128 * 64 * 2, LO32 = 128 * 32 * 2, LO16 = 128 * 16 * 2;
   const uint32_t aGEO = aCIN + GEO_CHUNK;  // [geo | 1] as a K=16 tile: hi at aGEO, lo at aGEO + LO64
   uint32_t phase = 0;
-  const bool issuer = tid == 0;
 
   const long long N = (long long)a.Rr.R * a.Rr.S;
-  const long long tiles = (N + kT - 1) / kT;
+  const long long tiles = (N + 127) / 128;
   const int S = a.Rr.S;
   const uint32_t hmask = (1u << F.log2T) - 1u;
 
-  // per-thread running sums of the narrow bias gradients
-  float acc_do3[3] = {0.f, 0.f, 0.f}, acc_dout[16], acc_dlogit = 0.f;
+  // per-thread running sums of the narrow bias gradients (half 0: do3, dlogit; half 1: dout16)
+  float acc_small[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) acc_dout[i] = 0.f;
+  for (int i = 0; i < 16; ++i) acc_small[i] = 0.f;
+  float acc_dlogit = 0.f;
   bool first = true;
 
 #define FNR_SYNC_ISSUE(...)            \
   fence_async_smem();                  \
   fence_before_sync();                 \
   __syncthreads();                     \
-  if (issuer) {                        \
-    fence_after_sync();                \
-    __VA_ARGS__;                       \
-    mma_commit(&s_bar);                \
+  if (warp == 0) {                     \
+    if (elect_one_sync()) {            \
+      fence_after_sync();              \
+      __VA_ARGS__;                     \
+      mma_commit(&s_bar);              \
+    }                                  \
+    __syncwarp();                      \
   }
 #define FNR_WAIT()          \
   mbar_wait(&s_bar, phase); \
   phase ^= 1;               \
   fence_after_sync();
 
+#pragma unroll 1
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const long long p = tile * kT + row;
+    const long long p = tile * 128 + row;
     const bool valid = p < N;
     const long long pc = valid ? p : N - 1;
     const int ray = (int)(pc / S);
@@ -261,24 +276,23 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
     const float vm = valid ? 1.f : 0.f;
     const float* pg = a.point_grads + 5 * (size_t)pc;
     const float d_sigma = __ldg(pg) * vm;
-    const float d_rgb[3] = {__ldg(pg + 1) * vm, __ldg(pg + 2) * vm, __ldg(pg + 3) * vm};
     const float d_logit = __ldg(pg + 4) * vm;
+    const float4* stash4 = reinterpret_cast<const float4*>(a.stash_encoding + (size_t)pc * ENC);
 
     // ---- T0: encoding tile (from the forward's stash) -> A ; base0 ------------------------------------
-    {
-      const float4* st = reinterpret_cast<const float4*>(a.stash_encoding + (size_t)pc * ENC);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 u = __ldg(st + 2 * j), w = __ldg(st + 2 * j + 1);
-        const float c[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
-        store_chunk(tA, 128 * 32 * 2, row, j, c);
-      }
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = 2 * half + jj;
+      const float4 u = __ldg(stash4 + 2 * j), w = __ldg(stash4 + 2 * j + 1);
+      const float c[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
+      store_chunk(tA, 128 * 32 * 2, row, j, c);
     }
     FNR_SYNC_ISSUE(issue_gemm<32, 64>(tb + C_R0, aA, sb + OFF_W0))
 
     // ---- T1: colour-input chunks [sh | app] ; h1 -> H ; base1 ------------------------------------------
     int cam = 0;
-    {
+    if (F.appearance_mode == FNR_APP_PER_CAMERA) cam = __ldg(a.Rr.camera_indices + ray);
+    if (half == 0) {
       float sh[SHD];
       sh_degree4(__ldg(d), __ldg(d + 1), __ldg(d + 2), sh);
 #pragma unroll
@@ -288,30 +302,23 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
         for (int q = 0; q < 8; ++q) c[q] = sh[8 * j + q];
         store_chunk(tCIN, 128 * 64 * 2, row, j, c);
       }
-      if (F.appearance_mode == FNR_APP_PER_CAMERA) {
-        cam = __ldg(a.Rr.camera_indices + ray);
-        const float4* e4 = reinterpret_cast<const float4*>(P.app_embedding + (size_t)cam * APP);
+    } else {
+      const float4* e4 = reinterpret_cast<const float4*>(P.app_embedding + (size_t)cam * APP);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 4; ++j) {
+        float c[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (F.appearance_mode == FNR_APP_PER_CAMERA) {
           const float4 u = __ldg(e4 + 2 * j), w = __ldg(e4 + 2 * j + 1);
-          const float c[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
-          store_chunk(tCIN, 128 * 64 * 2, row, 2 + j, c);
+          c[0] = u.x; c[1] = u.y; c[2] = u.z; c[3] = u.w; c[4] = w.x; c[5] = w.y; c[6] = w.z; c[7] = w.w;
         }
-      } else {  // FNR_APP_ZEROS
-        const float c[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) store_chunk(tCIN, 128 * 64 * 2, row, 2 + j, c);
+        store_chunk(tCIN, 128 * 64 * 2, row, 2 + j, c);
       }
     }
     FNR_WAIT()
-    {
-      float v[64];
-      load_row64<true>(trow + C_R0, sf + F_B0, v);
-      store_row64(tH, row, v);
-    }
+    epi32(trow + C_R0 + 32 * half, tH, row, half, [&](int n, float x) { return fmaxf(x + sf[F_B0 + n], 0.f); });
     FNR_SYNC_ISSUE(issue_gemm<64, 16>(tb + C_R1, aH, sb + OFF_W1))
 
-    // ---- T2: [h0 | geo] ; geo tiles ; dlogit tile ; semantic0 + colour0 --------------------------------
+    // ---- T2: [h0 | geo] ; geo chunks ; dlogit tile ; semantic0 + colour0 --------------------------------
     FNR_WAIT()
     float d_h0;
     {
@@ -323,97 +330,99 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
       for (int n = 0; n < 16; ++n) outv[n] = __uint_as_float(r0[n]) + sf[F_B1 + n];
       // density = exp(h0) * selector ; trunc_exp backward: g * exp(clamp(h0, -15, 15))
       d_h0 = sel ? d_sigma * expf(fminf(fmaxf(outv[0], -15.f), 15.f)) : 0.f;
-      float g0[8], g1[8];
+      float g[8];
+      if (half == 0) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        g0[q] = outv[1 + q];
-        g1[q] = q < 7 ? outv[9 + q] : 1.0f;  // column 15 / 63 = 1: bias-gradient column
+        for (int q = 0; q < 8; ++q) g[q] = outv[1 + q];
+        store_chunk(tCIN, 128 * 64 * 2, row, 6, g);
+        const float dl0[8] = {d_logit, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        store_chunk(tD16, 128 * 16 * 2, row, 0, dl0);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) g[q] = q < 7 ? outv[9 + q] : 1.0f;  // column 63 (= 15 of [geo|1]) = 1: bias-gradient column
+        store_chunk(tCIN, 128 * 64 * 2, row, 7, g);
+        const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        store_chunk(tD16, 128 * 16 * 2, row, 1, z8);
       }
-      store_chunk(tCIN, 128 * 64 * 2, row, 6, g0);
-      store_chunk(tCIN, 128 * 64 * 2, row, 7, g1);
-      const float dl0[8] = {d_logit, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      store_chunk(tD16, 128 * 16 * 2, row, 0, dl0);
-      store_chunk(tD16, 128 * 16 * 2, row, 1, z8);
     }
     FNR_SYNC_ISSUE(issue_gemm_lo<16, 64>(tb + C_R2, aGEO, aGEO + LO64, sb + OFF_WS0); issue_gemm<64, 64>(tb + C_R0, aCIN, sb + OFF_WC0))
 
-    // ---- T3: z1 -> A, c1 -> C1, dz1 -> DY ; colour1 + AV + AS0 ----------------------------------------
+    // ---- T3: z1 -> A, dz1 -> DY, c1 -> C1 ; colour1 + AV + AS0 ----------------------------------------
     FNR_WAIT()
     {
-      float v[64];
-      load_row64<true>(trow + C_R2, sf + F_BS0, v);
-      store_row64(tA, row, v);
+      uint32_t r[4][8];
 #pragma unroll
-      for (int n = 0; n < 64; ++n) v[n] = v[n] > 0.f ? d_logit * sf[F_FOLD + n] : 0.f;
-      store_row64(tDY, row, v);
-      load_row64<true>(trow + C_R0, sf + F_BC0, v);
-      store_row64(tC1, row, v);
+      for (int j = 0; j < 4; ++j) tmem_ld8(trow + C_R2 + 32 * half + 8 * j, r[j]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float z[8], dz[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int n = 32 * half + 8 * j + q;
+          z[q] = fmaxf(__uint_as_float(r[j][q]) + sf[F_BS0 + n], 0.f);
+          dz[q] = z[q] > 0.f ? d_logit * sf[F_FOLD + n] : 0.f;
+        }
+        store_chunk(tA, 128 * 64 * 2, row, 4 * half + j, z);
+        store_chunk(tDY, 128 * 64 * 2, row, 4 * half + j, dz);
+      }
     }
+    epi32(trow + C_R0 + 32 * half, tC1, row, half, [&](int n, float x) { return fmaxf(x + sf[F_BC0 + n], 0.f); });
     FNR_SYNC_ISSUE(issue_gemm<64, 64>(tb + C_R0, aC1, sb + OFF_WC1); issue_dw<16>(tb + C_AV, aA, aA + LO64, aD16, aD16 + LO16, !first);
                    issue_dw<16>(tb + C_AS0, aDY, aDY + LO64, aGEO, aGEO + LO64, !first))
 
     // ---- T4: c2 -> A ; do3 -> D16 ; AC2 + dc2 -----------------------------------------------------------
     FNR_WAIT()
-    float do3[3];
-    {
-      float v[64];
-      load_row64<true>(trow + C_R0, sf + F_BC1, v);
-      store_row64(tA, row, v);
+    epi32(trow + C_R0 + 32 * half, tA, row, half, [&](int n, float x) { return fmaxf(x + sf[F_BC1 + n], 0.f); });
+    if (half == 0) {
       const float* rgb = a.sample_rgb + 3 * (size_t)pc;
+      float do3[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         const float c = __ldg(rgb + i);
-        do3[i] = d_rgb[i] * c * (1.0f - c);
+        do3[i] = __ldg(pg + 1 + i) * vm * c * (1.0f - c);
+        acc_small[i] += do3[i];
       }
-      const float c0[8] = {do3[0], do3[1], do3[2], 0.f, 0.f, 0.f, 0.f, 0.f}, z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      acc_dlogit += d_logit;
+      const float c0[8] = {do3[0], do3[1], do3[2], 0.f, 0.f, 0.f, 0.f, 0.f};
       store_chunk(tD16, 128 * 16 * 2, row, 0, c0);
+    } else {
+      const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       store_chunk(tD16, 128 * 16 * 2, row, 1, z8);
     }
     FNR_SYNC_ISSUE(issue_dw<16>(tb + C_AC2, aA, aA + LO64, aD16, aD16 + LO16, !first); issue_dx<16, 64>(tb + C_R2, aD16, sb + OFF_WC2))
 
     // ---- T5: dc2 = (do3 Wc2) * relu'(c2) -> DY ; AC1, AC1b, dc1 ----------------------------------------
     FNR_WAIT()
-    {
-      float v[64];
-      load_row64<false>(trow + C_R2, nullptr, v);
-      const unsigned long long m = relu_mask64(tA, row);
-#pragma unroll
-      for (int n = 0; n < 64; ++n) v[n] = ((m >> n) & 1ull) ? v[n] : 0.f;
-      store_row64(tDY, row, v);
-    }
+    epi32_masked(trow + C_R2 + 32 * half, tA, tDY, row, half);
     FNR_SYNC_ISSUE(issue_dw<64>(tb + C_AC1, aDY, aDY + LO64, aC1, aC1 + LO64, !first); issue_dw<16>(tb + C_AC1B, aDY, aDY + LO64, aONES, 0u, !first);
                    issue_dx<64, 64>(tb + C_R0, aDY, sb + OFF_WC1))
 
     // ---- T6: dc1 = (dc2 Wc1) * relu'(c1) -> DY ; AC0, dcin --------------------------------------------
     FNR_WAIT()
-    {
-      float v[64];
-      load_row64<false>(trow + C_R0, nullptr, v);
-      const unsigned long long m = relu_mask64(tC1, row);
-#pragma unroll
-      for (int n = 0; n < 64; ++n) v[n] = ((m >> n) & 1ull) ? v[n] : 0.f;
-      store_row64(tDY, row, v);
-    }
+    epi32_masked(trow + C_R0 + 32 * half, tC1, tDY, row, half);
     FNR_SYNC_ISSUE(issue_dw<64>(tb + C_AC0, aDY, aDY + LO64, aCIN, aCIN + LO64, !first); issue_dx<64, 64>(tb + C_R2, aDY, sb + OFF_WC0))
 
     // ---- T7: dcin -> d_app (embedding gradient), d_geo ; dout16 -> D16 ; AB1, dh1 -----------------------
     FNR_WAIT()
-    float dout[16];
     {
-      float v[64];
-      load_row64<false>(trow + C_R2, nullptr, v);
+      // half 0: columns 16..31 = d_app[0..15];  half 1: columns 32..47 = d_app[16..31], 48..62 = d_geo
+      uint32_t ra[16], rg[16];
+      tmem_ld16(trow + C_R2 + 16 + 16 * half, ra);
+      if (half == 1) tmem_ld16(trow + C_R2 + 48, rg);
+      tmem_ld_wait();
       if (F.appearance_mode == FNR_APP_PER_CAMERA) {
         const bool uniform = __all_sync(kTcFullMask, cam == __shfl_sync(kTcFullMask, cam, 0));
         if (uniform) {
-          // transposed butterfly: lane j ends with sum over the warp of d_app[j]
-          float w[32];
+          // transposed butterfly over 16 values: after offsets 16,8,4,2 lane L holds (half-)sums of value L>>1
+          float w[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) w[i] = v[SHD + i];
+          for (int i = 0; i < 16; ++i) w[i] = __uint_as_float(ra[i]);
 #pragma unroll
-          for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+          for (int off = 16, n = 8; off >= 2; off >>= 1, n >>= 1) {
             const bool hi = (lane & off) != 0;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
+            for (int i = 0; i < 8; ++i) {
               if (i < n) {
                 const float send = hi ? w[i] : w[i + n];
                 const float keep = hi ? w[i + n] : w[i];
@@ -421,70 +430,67 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
               }
             }
           }
-          if (w[0] != 0.f) atomicAdd(G.app_embedding + (size_t)cam * APP + lane, w[0]);
+          const float tot = w[0] + __shfl_xor_sync(kTcFullMask, w[0], 1);
+          if ((lane & 1) == 0 && tot != 0.f) atomicAdd(G.app_embedding + (size_t)cam * APP + 16 * half + (lane >> 1), tot);
         } else {
 #pragma unroll
-          for (int i = 0; i < APP; ++i)
-            if (v[SHD + i] != 0.f) atomicAdd(G.app_embedding + (size_t)cam * APP + i, v[SHD + i]);
+          for (int i = 0; i < 16; ++i) {
+            const float v = __uint_as_float(ra[i]);
+            if (v != 0.f) atomicAdd(G.app_embedding + (size_t)cam * APP + 16 * half + i, v);
+          }
         }
       }
-      dout[0] = d_h0;
+      if (half == 1) {
+        float c0[8], c1[8];
+        c0[0] = d_h0;
 #pragma unroll
-      for (int i = 0; i < GEO; ++i) dout[1 + i] = v[SHD + APP + i];
-      float c0[8], c1[8];
+        for (int q = 1; q < 8; ++q) c0[q] = __uint_as_float(rg[q - 1]);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        c0[q] = dout[q];
-        c1[q] = dout[8 + q];
+        for (int q = 0; q < 8; ++q) c1[q] = __uint_as_float(rg[7 + q]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          acc_small[q] += c0[q];
+          acc_small[8 + q] += c1[q];
+        }
+        store_chunk(tD16, 128 * 16 * 2, row, 0, c0);
+        store_chunk(tD16, 128 * 16 * 2, row, 1, c1);
       }
-      store_chunk(tD16, 128 * 16 * 2, row, 0, c0);
-      store_chunk(tD16, 128 * 16 * 2, row, 1, c1);
     }
     FNR_SYNC_ISSUE(issue_dw<16>(tb + C_AB1, aH, aH + LO64, aD16, aD16 + LO16, !first); issue_dx<16, 64>(tb + C_R0, aD16, sb + OFF_W1))
 
     // ---- T8: dh1 = (dout W1) * relu'(h1) -> DY ; reload enc -> A ; AB0, AB0b, denc ------------------------
     FNR_WAIT()
-    {
-      float v[64];
-      load_row64<false>(trow + C_R0, nullptr, v);
-      const unsigned long long m = relu_mask64(tH, row);
+    epi32_masked(trow + C_R0 + 32 * half, tH, tDY, row, half);
 #pragma unroll
-      for (int n = 0; n < 64; ++n) v[n] = ((m >> n) & 1ull) ? v[n] : 0.f;
-      store_row64(tDY, row, v);
-      const float4* st = reinterpret_cast<const float4*>(a.stash_encoding + (size_t)pc * ENC);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 u = __ldg(st + 2 * j), w = __ldg(st + 2 * j + 1);
-        const float c[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
-        store_chunk(tA, 128 * 32 * 2, row, j, c);
-      }
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = 2 * half + jj;
+      const float4 u = __ldg(stash4 + 2 * j), w = __ldg(stash4 + 2 * j + 1);
+      const float c[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
+      store_chunk(tA, 128 * 32 * 2, row, j, c);
     }
     FNR_SYNC_ISSUE(issue_dw<32>(tb + C_AB0, aDY, aDY + LO64, aA, aA + LO32, !first); issue_dw<16>(tb + C_AB0B, aDY, aDY + LO64, aONES, 0u, !first);
                    issue_dx<64, 32>(tb + C_R2, aDY, sb + OFF_W0))
 
-    // ---- T9: denc -> hash-table gradient scatter -------------------------------------------------------
-#pragma unroll
-    for (int i = 0; i < 3; ++i) acc_do3[i] += do3[i];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) acc_dout[i] += dout[i];
-    acc_dlogit += d_logit;
+    // ---- T9: denc -> hash-table gradient scatter (this thread: levels 8*half .. 8*half+7) ----------------
     FNR_WAIT()
     {
-      uint32_t r0[32];
-      tmem_ld32(trow + C_R2, r0);
+      uint32_t r0[16];
+      tmem_ld16(trow + C_R2 + 16 * half, r0);
       tmem_ld_wait();
-      if (valid) {
+      if (valid && !(a.debug_flags & 1)) {
         float2* gt = reinterpret_cast<float2*>(G.hash_table);
-#pragma unroll 1
-        for (int l = 0; l < 16; ++l) {
-          const float g0 = __uint_as_float(r0[2 * l]), g1 = __uint_as_float(r0[2 * l + 1]);
-          if (g0 == 0.f && g1 == 0.f) continue;
-          const LevelCell c = level_cell(pos, F.scalings[l]);
-          const uint32_t base = (uint32_t)l << F.log2T;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float w = corner_weight(c, k);
-            if (w != 0.f) atomicAdd(gt + corner_row(c, k, hmask, base), make_float2(w * g0, w * g1));
+        for (int li = 0; li < 8; ++li) {
+          const int l = 8 * half + li;
+          const float g0 = __uint_as_float(r0[2 * li]), g1 = __uint_as_float(r0[2 * li + 1]);
+          if (g0 != 0.f || g1 != 0.f) {
+            const LevelCell c = level_cell(pos, F.scalings[l]);
+            const uint32_t base = (uint32_t)l << F.log2T;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float w = corner_weight(c, k);
+              if (w != 0.f) atomicAdd(gt + corner_row(c, k, hmask, base), make_float2(w * g0, w * g1));
+            }
           }
         }
       }
@@ -500,117 +506,100 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
   __syncthreads();
   fence_after_sync();
   if (!first) {
-    // M=64 accumulators: row i lives in TMEM lane (i % 16) + 32 * (i / 16)  ->  this thread: lane < 16, i = 16*warp + lane
+    // M=64 accumulators: row i lives in TMEM lane (i % 16) + 32 * (i / 16)  ->  owner threads: lane < 16,
+    // i = 16 * (warp & 3) + lane; the two halves split the columns of every accumulator.
     const bool owner = lane < 16;
-    const int i = 16 * warp + lane;
-    uint32_t r[32];
-    // AV: v[i] = sum_points z1[i] * dlogit -> shared scratch
-    {
+    const int i = 16 * (warp & 3) + lane;
+    {  // AV: v[i] = sum_points z1[i] * dlogit -> shared scratch ;  AS0 ; AC2 ; AB1   (16-column accumulators)
       uint32_t q[8];
       tmem_ld8(trow + C_AV, q);
       tmem_ld_wait();
-      if (owner) sf[F_RED + i] = __uint_as_float(q[0]);
-    }
-    // AS0: d W_sem0[n=i][k<15], column 15 = d b_sem0[i]
-    {
-      uint32_t q[16];
-      tmem_ld16(trow + C_AS0, q);
+      if (owner && half == 0) sf[F_RED + i] = __uint_as_float(q[0]);
+      tmem_ld8(trow + C_AS0 + 8 * half, q);  // d W_sem0[n=i][k<15], column 15 = d b_sem0[i]
       tmem_ld_wait();
       if (owner) {
 #pragma unroll
-        for (int k = 0; k < GEO; ++k) atomicAdd(G.sem_w[0] + i * GEO + k, __uint_as_float(q[k]));
-        atomicAdd(G.sem_b[0] + i, __uint_as_float(q[15]));
+        for (int kk = 0; kk < 8; ++kk) {
+          const int k = 8 * half + kk;
+          if (k < GEO) atomicAdd(G.sem_w[0] + i * GEO + k, __uint_as_float(q[kk]));
+          else atomicAdd(G.sem_b[0] + i, __uint_as_float(q[kk]));
+        }
       }
-    }
-    // AC2: rows = c2 feature k=i, cols = colour output n<3
-    {
-      uint32_t q[8];
-      tmem_ld8(trow + C_AC2, q);
+      tmem_ld8(trow + C_AC2, q);  // rows = c2 feature k=i, cols = colour output n<3
       tmem_ld_wait();
-      if (owner) {
+      if (owner && half == 0) {
 #pragma unroll
         for (int n = 0; n < 3; ++n) atomicAdd(G.col_w[2] + n * H + i, __uint_as_float(q[n]));
       }
-    }
-    // AC1 / AC1b
-    {
+      tmem_ld8(trow + C_AB1 + 8 * half, q);  // rows = h1 feature k=i, cols = base output n<16
+      tmem_ld_wait();
+      if (owner) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        tmem_ld32(trow + C_AC1 + 32 * half, r);
-        tmem_ld_wait();
-        if (owner) {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) atomicAdd(G.col_w[1] + i * H + 32 * half + k, __uint_as_float(r[k]));
-        }
+        for (int kk = 0; kk < 8; ++kk) atomicAdd(G.base_w[1] + (8 * half + kk) * H + i, __uint_as_float(q[kk]));
       }
-      uint32_t q[8];
       tmem_ld8(trow + C_AC1B, q);
       tmem_ld_wait();
-      if (owner) atomicAdd(G.col_b[1] + i, __uint_as_float(q[0]));
-    }
-    // AC0: cols in [sh | app | geo | bias] order -> torch order [sh | geo | app]
-    {
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        tmem_ld32(trow + C_AC0 + 32 * half, r);
-        tmem_ld_wait();
-        if (owner) {
-          float* gw = G.col_w[0] + i * (SHD + GEO + APP);
-#pragma unroll
-          for (int kk = 0; kk < 32; ++kk) {
-            const int k = 32 * half + kk;
-            const float val = __uint_as_float(r[kk]);
-            if (k < SHD) atomicAdd(gw + k, val);
-            else if (k < SHD + APP) atomicAdd(gw + SHD + GEO + (k - SHD), val);
-            else if (k < SHD + APP + GEO) atomicAdd(gw + SHD + (k - SHD - APP), val);
-            else atomicAdd(G.col_b[0] + i, val);
-          }
-        }
-      }
-    }
-    // AB1: rows = h1 feature k=i, cols = base output n<16
-    {
-      uint32_t q[16];
-      tmem_ld16(trow + C_AB1, q);
-      tmem_ld_wait();
-      if (owner) {
-#pragma unroll
-        for (int n = 0; n < 16; ++n) atomicAdd(G.base_w[1] + n * H + i, __uint_as_float(q[n]));
-      }
-    }
-    // AB0 / AB0b
-    {
-      tmem_ld32(trow + C_AB0, r);
-      tmem_ld_wait();
-      if (owner) {
-#pragma unroll
-        for (int k = 0; k < 32; ++k) atomicAdd(G.base_w[0] + i * ENC + k, __uint_as_float(r[k]));
-      }
-      uint32_t q[8];
+      if (owner && half == 0) atomicAdd(G.col_b[1] + i, __uint_as_float(q[0]));
       tmem_ld8(trow + C_AB0B, q);
       tmem_ld_wait();
-      if (owner) atomicAdd(G.base_b[0] + i, __uint_as_float(q[0]));
+      if (owner && half == 1) atomicAdd(G.base_b[0] + i, __uint_as_float(q[0]));
+    }
+    uint32_t r[32];
+    // AC1: d W_col1[n=i][k]
+    tmem_ld32(trow + C_AC1 + 32 * half, r);
+    tmem_ld_wait();
+    if (owner) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) atomicAdd(G.col_w[1] + i * H + 32 * half + k, __uint_as_float(r[k]));
+    }
+    // AC0: cols in [sh | app | geo | bias] order -> torch order [sh | geo | app]
+    tmem_ld32(trow + C_AC0 + 32 * half, r);
+    tmem_ld_wait();
+    if (owner) {
+      float* gw = G.col_w[0] + i * (SHD + GEO + APP);
+#pragma unroll
+      for (int kk = 0; kk < 32; ++kk) {
+        const int k = 32 * half + kk;
+        const float val = __uint_as_float(r[kk]);
+        if (k < SHD) atomicAdd(gw + k, val);
+        else if (k < SHD + APP) atomicAdd(gw + SHD + GEO + (k - SHD), val);
+        else if (k < SHD + APP + GEO) atomicAdd(gw + SHD + (k - SHD - APP), val);
+        else atomicAdd(G.col_b[0] + i, val);
+      }
+    }
+    // AB0: d W_base0[n=i][k<32]
+    {
+      uint32_t q[16];
+      tmem_ld16(trow + C_AB0 + 16 * half, q);
+      tmem_ld_wait();
+      if (owner) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) atomicAdd(G.base_w[0] + i * ENC + 16 * half + k, __uint_as_float(q[k]));
+      }
     }
     // narrow bias gradients + sum of dlogit: warp reduce, then one atomic per warp
+    if (half == 0) {
 #pragma unroll
-    for (int n = 0; n < 3; ++n) {
-      const float s = warp_sum_f(acc_do3[n]);
-      if (lane == 0) atomicAdd(G.col_b[2] + n, s);
-    }
+      for (int n = 0; n < 3; ++n) {
+        const float s = warp_sum_f(acc_small[n]);
+        if (lane == 0) atomicAdd(G.col_b[2] + n, s);
+      }
+      const float sdl_w = warp_sum_f(acc_dlogit);
+      if (lane == 0) sf[F_RED + 64 + warp] = sdl_w;
+    } else {
 #pragma unroll
-    for (int n = 0; n < 16; ++n) {
-      const float s = warp_sum_f(acc_dout[n]);
-      if (lane == 0) atomicAdd(G.base_b[1] + n, s);
+      for (int n = 0; n < 16; ++n) {
+        const float s = warp_sum_f(acc_small[n]);
+        if (lane == 0) atomicAdd(G.base_b[1] + n, s);
+      }
     }
-    const float sdl_w = warp_sum_f(acc_dlogit);
-    if (lane == 0) sf[F_RED + 64 + warp] = sdl_w;
   }
   __syncthreads();
   if (!first) {
     // folded semantic tail: logit = head_w . (W1 z1 + b1) + head_b, with v = sum dlogit * z1, s = sum dlogit
     const float* v = sf + F_RED;
     float sdl = 0.f;
-    for (int w = 0; w < kT / 32; ++w) sdl += sf[F_RED + 64 + w];
+    for (int w = 0; w < 4; ++w) sdl += sf[F_RED + 64 + w];
     if (tid == 0) atomicAdd(G.head_b, sdl);
     if (tid < H) {
       const int j = tid;
@@ -660,7 +649,17 @@ int launch_tc_field_backward(Family fam, const KField& F, const KParams& P, cons
   a.point_grads = B.point_grads;
   a.stash_encoding = B.stash_encoding;
   a.sample_rgb = B.sample_rgb;
-  const long long tiles = (N + kT - 1) / kT;
+  {
+    static int flags = -1;
+    if (flags < 0) {
+      const char* e = getenv("FNR_DEBUG_BWD");
+      flags = e ? atoi(e) : 0;
+      const int skip = (flags >> 1) & 1;
+      cudaMemcpyToSymbol(g_skip_dw, &skip, sizeof(int));
+    }
+    a.debug_flags = flags;
+  }
+  const long long tiles = (N + 127) / 128;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   tc_field_backward_kernel<<<grid, kT, kSmem, st>>>(a);
   return check_cuda(cudaGetLastError(), "tc_field_backward_kernel");
