@@ -4,8 +4,10 @@
 //
 // Work decomposition
 //   * A CTA owns a group of G whole rays (G*S <= kMaxGroupPoints) at a time; its points are processed
-//     in rounds of kSlots*128 points.  A "slot" is 4 warps = 128 threads = the 128 rows (TMEM lanes)
-//     of an M=128 MMA tile; thread r of a slot owns point r of the tile from the gather to the heads.
+//     in rounds of kSlots*128 points.  A "slot" is 8 warps = 256 threads serving the 128 rows (TMEM lanes)
+//     of an M=128 MMA tile: the thread pair (r, r+128) owns point r from the gather to the heads, one
+//     thread taking hash levels 0-7 / accumulator columns 0-31, the other levels 8-15 / columns 32-63
+//     (two warps may address the same TMEM lane quarter), which doubles the loads in flight per point.
 //     Slots only meet at the per-group compositing step, so one slot's gathers overlap the other
 //     slot's tensor-core round trips.
 //   * Gather: per level 8 float2 loads (read-only path), trilinear blend in registers, 32 features.
@@ -32,7 +34,8 @@ using namespace tcx;
 namespace {
 
 constexpr int kSlots = 2;
-constexpr int kCtaThreads = kSlots * 128;
+constexpr int kSlotThreads = 256;  // 2 threads per point (column / level halves)
+constexpr int kCtaThreads = kSlots * kSlotThreads;
 constexpr int kMaxGroupPoints = 768;
 constexpr int kTmemColsPerSlot = 160;
 constexpr unsigned kFullMask = kTcFullMask;
@@ -84,6 +87,22 @@ struct TcArgs {
   int composite;
 };
 
+// 32-column epilogue of the thread pair (row, half): v = f(column, accumulator) -> chunks 4*half.. of a K=64 tile.
+template <class Fn>
+__device__ __forceinline__ void epi32(uint32_t taddr32, uint8_t* tile, int row, int half, Fn f) {
+  uint32_t r[4][8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) tmem_ld8(taddr32 + 8 * j, r[j]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float c[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) c[q] = f(32 * half + 8 * j + q, __uint_as_float(r[j][q]));
+    store_chunk(tile, 128 * 64 * 2, row, 4 * half + j, c);
+  }
+}
+
 __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -91,8 +110,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
   __shared__ uint32_t s_tmem_base;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int slot = warp >> 2;
-  const int row = (warp & 3) * 32 + lane;  // TMEM lane of this thread (warp w may touch lanes 32*(w%4)..)
+  const int slot = warp >> 3;              // 8 warps per slot
+  const int half = (warp >> 2) & 1;        // which 32 of 64 accumulator columns / which 8 of 16 levels
+  const int row = (warp & 3) * 32 + lane;  // TMEM lane = point of this thread pair (warp w may touch lanes 32*(w%4)..)
   const KParams& P = a.P;
   const KField& F = a.F;
   float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
@@ -159,7 +179,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
   const uint32_t wBase = smem_u32(smem);
   uint64_t* bar = &s_bar[slot];
   uint32_t phase = 0;
-  const bool issue_warp = (warp & 3) == 0;
+  const bool issue_warp = (warp & 7) == 0;
   const int bar_id = 1 + slot;
 
   const int S = a.Rr.S, R = a.Rr.R;
@@ -168,14 +188,32 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
   const float2* __restrict__ table = reinterpret_cast<const float2*>(P.hash_table);
   const uint32_t hmask = (1u << F.log2T) - 1u;
 
+#define FNR_SLOT_ISSUE(...)              \
+  fence_async_smem();                    \
+  fence_before_sync();                   \
+  named_bar_sync(bar_id, kSlotThreads);  \
+  if (issue_warp) {                      \
+    if (elect_one_sync()) {              \
+      fence_after_sync();                \
+      __VA_ARGS__;                       \
+      mma_commit(bar);                   \
+    }                                    \
+    __syncwarp();                        \
+  }
+#define FNR_SLOT_WAIT()  \
+  mbar_wait(bar, phase); \
+  phase ^= 1;            \
+  fence_after_sync();
+
   for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
     const int ray0 = group * G;
     const int rays_here = min(G, R - ray0);
     const int pts = rays_here * S;
-    const int rounds = (pts + kCtaThreads - 1) / kCtaThreads;
+    const int rounds = (pts + kSlots * 128 - 1) / (kSlots * 128);
 
+#pragma unroll 1
     for (int rd = 0; rd < rounds; ++rd) {
-      const int local = rd * kCtaThreads + slot * 128 + row;  // point index inside the group
+      const int local = rd * (kSlots * 128) + slot * 128 + row;  // point index inside the group
       const bool valid = local < pts;
       const int lc = valid ? local : pts - 1;
       const int ray = ray0 + lc / S;
@@ -185,225 +223,114 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
       bool sel;
       const Vec3 pos = field_position(o, d, __ldg(a.Rr.starts + gp), __ldg(a.Rr.ends + gp), F.position_mode, F.aabb, sel);
 
-      // ---- gather + trilinear blend -> encoding tile (aliases Q) -----------------------------
+      // ---- gather + trilinear blend: this thread's 8 levels -> chunks 2*half, 2*half+1 of the encoding tile (aliases Q)
       {
-        float enc[ENC];
+        float enc[16];
 #pragma unroll
-        for (int l = 0; l < 16; ++l) {
+        for (int li = 0; li < 8; ++li) {
+          const int l = 8 * half + li;
           const LevelCell c = level_cell(pos, F.scalings[l]);
           const uint32_t base = (uint32_t)l << F.log2T;
           float2 f[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) f[k] = __ldg(table + corner_row(c, k, hmask, base));
           const float2 r = trilerp(f, c);
-          enc[2 * l] = r.x;
-          enc[2 * l + 1] = r.y;
+          enc[2 * li] = r.x;
+          enc[2 * li + 1] = r.y;
         }
         if (a.O.stash_encoding && valid) {
-          float4* st = reinterpret_cast<float4*>(a.O.stash_encoding + gp * ENC);
+          float4* st = reinterpret_cast<float4*>(a.O.stash_encoding + gp * ENC + 16 * half);
 #pragma unroll
-          for (int i = 0; i < ENC / 4; ++i) st[i] = make_float4(enc[4 * i], enc[4 * i + 1], enc[4 * i + 2], enc[4 * i + 3]);
+          for (int i = 0; i < 4; ++i) st[i] = make_float4(enc[4 * i], enc[4 * i + 1], enc[4 * i + 2], enc[4 * i + 3]);
         }
 #pragma unroll
-        for (int j = 0; j < K_BASE0 / 8; ++j) {
+        for (int jj = 0; jj < 2; ++jj) {
           float v[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) v[q] = enc[8 * j + q];
-          store_chunk(tQ, 128 * K_BASE0 * 2, row, j, v);
+          for (int q = 0; q < 8; ++q) v[q] = enc[8 * jj + q];
+          store_chunk(tQ, 128 * K_BASE0 * 2, row, 2 * half + jj, v);
         }
       }
-      fence_async_smem();
-      fence_before_sync();
-      named_bar_sync(bar_id, 128);
-      if (issue_warp) {
-        if (elect_one_sync()) {
-          fence_after_sync();
-          issue_gemm<K_BASE0, N_BASE0>(tmem_slot + C_R0, aQ, wBase + OFF_W_BASE0);
-          mma_commit(bar);
-        }
-        __syncwarp();
-      }
+      FNR_SLOT_ISSUE(issue_gemm<K_BASE0, N_BASE0>(tmem_slot + C_R0, aQ, wBase + OFF_W_BASE0))
 
-      // ---- epilogue 1: h1 = relu(base0 + b) -> P ; sh / appearance part of the colour input -> Q later
-      float sh[SHD], app[APP];
-      sh_degree4(__ldg(d), __ldg(d + 1), __ldg(d + 2), sh);
-      if (F.appearance_mode == FNR_APP_PER_CAMERA) {
-        const float4* e4 = reinterpret_cast<const float4*>(P.app_embedding + (size_t)__ldg(a.Rr.camera_indices + ray) * APP);
+      // ---- epilogue 1: h1 = relu(base0 + b) -> P ; then the geo-independent colour-input chunks -> Q ------
+      FNR_SLOT_WAIT()
+      epi32(tmem_row + C_R0 + 32 * half, tP, row, half, [&](int n, float x) { return fmaxf(x + s_bias[B_BASE0 + n], 0.f); });
+      FNR_SLOT_ISSUE(issue_gemm<K_BASE1, N_BASE1>(tmem_slot + C_R1, aP, wBase + OFF_W_BASE1))
+      // colour input K order [sh 0..15 | app 0..31 | geo | 0]: chunks 0,1 = sh (half 0), 2..5 = app (half 1).
+      // (the encoding tile in Q is dead: its GEMM completed before epilogue 1 ran)
+      if (half == 0) {
+        float sh[SHD];
+        sh_degree4(__ldg(d), __ldg(d + 1), __ldg(d + 2), sh);
 #pragma unroll
-        for (int i = 0; i < APP / 4; ++i) {
-          const float4 v = __ldg(e4 + i);
-          app[4 * i] = v.x;
-          app[4 * i + 1] = v.y;
-          app[4 * i + 2] = v.z;
-          app[4 * i + 3] = v.w;
+        for (int j = 0; j < 2; ++j) {
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = sh[8 * j + q];
+          store_chunk(tQ, 128 * 64 * 2, row, j, v);
         }
       } else {
+        const float* app = (F.appearance_mode == FNR_APP_PER_CAMERA)
+                               ? P.app_embedding + (size_t)__ldg(a.Rr.camera_indices + ray) * APP
+                               : nullptr;
 #pragma unroll
-        for (int i = 0; i < APP; ++i) app[i] = s_bias[B_APP + i];
-      }
-      mbar_wait(bar, phase);
-      phase ^= 1;
-      fence_after_sync();
-      {
-        uint32_t r0[32], r1[32];
-        tmem_ld32(tmem_row + C_R0, r0);
-        tmem_ld32(tmem_row + C_R0 + 32, r1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
           float v[8];
+          if (app) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(app) + 2 * j), w = __ldg(reinterpret_cast<const float4*>(app) + 2 * j + 1);
+            v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w; v[4] = w.x; v[5] = w.y; v[6] = w.z; v[7] = w.w;
+          } else {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int n = 8 * j + q;
-            const float x = __uint_as_float(n < 32 ? r0[n] : r1[n - 32]) + s_bias[B_BASE0 + n];
-            v[q] = fmaxf(x, 0.f);
+            for (int q = 0; q < 8; ++q) v[q] = s_bias[B_APP + 8 * j + q];
           }
-          store_chunk(tP, 128 * 64 * 2, row, j, v);
+          store_chunk(tQ, 128 * 64 * 2, row, 2 + j, v);
         }
-      }
-      fence_async_smem();
-      fence_before_sync();
-      named_bar_sync(bar_id, 128);
-      if (issue_warp) {
-        if (elect_one_sync()) {
-          fence_after_sync();
-          issue_gemm<K_BASE1, N_BASE1>(tmem_slot + C_R1, aP, wBase + OFF_W_BASE1);
-          mma_commit(bar);
-        }
-        __syncwarp();
-      }
-      // colour-input chunks that do not depend on geo: [sh 0..15 | app 0..31] = chunks 0..5 of Q
-      // (the encoding tile in Q is dead: its GEMM completed before epilogue 1 ran)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        float v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = sh[8 * j + q];
-        store_chunk(tQ, 128 * 64 * 2, row, j, v);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = app[8 * j + q];
-        store_chunk(tQ, 128 * 64 * 2, row, 2 + j, v);
       }
 
       // ---- epilogue 2: [h0 | geo] ; density ; geo -> S (semantic input) and chunks 6,7 of Q --------
-      mbar_wait(bar, phase);
-      phase ^= 1;
-      fence_after_sync();
-      float density;
+      FNR_SLOT_WAIT()
+      float density = 0.f;
       {
         uint32_t r0[16];
         tmem_ld16(tmem_row + C_R1, r0);
         tmem_ld_wait();
-        float outv[16];
+        float g[8];
+        if (half == 0) {
+          density = sel ? expf(__uint_as_float(r0[0]) + s_bias[B_BASE1]) : 0.f;
 #pragma unroll
-        for (int n = 0; n < 16; ++n) outv[n] = __uint_as_float(r0[n]) + s_bias[B_BASE1 + n];
-        density = sel ? expf(outv[0]) : 0.f;
-        float g0[8], g1[8];
+          for (int q = 0; q < 8; ++q) g[q] = __uint_as_float(r0[1 + q]) + s_bias[B_BASE1 + 1 + q];
+        } else {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          g0[q] = outv[1 + q];
-          g1[q] = q < 7 ? outv[9 + q] : 0.f;
+          for (int q = 0; q < 8; ++q) g[q] = q < 7 ? __uint_as_float(r0[9 + q]) + s_bias[B_BASE1 + 9 + q] : 0.f;
         }
-        store_chunk(tS, 128 * 16 * 2, row, 0, g0);
-        store_chunk(tS, 128 * 16 * 2, row, 1, g1);
-        store_chunk(tQ, 128 * 64 * 2, row, 6, g0);
-        store_chunk(tQ, 128 * 64 * 2, row, 7, g1);
+        store_chunk(tS, 128 * 16 * 2, row, half, g);
+        store_chunk(tQ, 128 * 64 * 2, row, 6 + half, g);
       }
-      fence_async_smem();
-      fence_before_sync();
-      named_bar_sync(bar_id, 128);
-      if (issue_warp) {
-        if (elect_one_sync()) {
-          fence_after_sync();
-          issue_gemm<K_SEM0, N_SEM0>(tmem_slot + C_R2, aS, wBase + OFF_W_SEM0);
-          issue_gemm<K_COL0, N_COL0>(tmem_slot + C_R0, aQ, wBase + OFF_W_COL0);
-          mma_commit(bar);
-        }
-        __syncwarp();
-      }
+      FNR_SLOT_ISSUE(issue_gemm<K_SEM0, N_SEM0>(tmem_slot + C_R2, aS, wBase + OFF_W_SEM0);
+                     issue_gemm<K_COL0, N_COL0>(tmem_slot + C_R0, aQ, wBase + OFF_W_COL0))
 
       // ---- epilogue 3: z1 = relu(sem0 + b) -> P ; c1 = relu(col0 + b) -> Q -------------------------
-      mbar_wait(bar, phase);
-      phase ^= 1;
-      fence_after_sync();
-#pragma unroll
-      for (int which = 0; which < 2; ++which) {
-        uint32_t r0[32], r1[32];
-        const uint32_t col = which == 0 ? C_R2 : C_R0;
-        tmem_ld32(tmem_row + col, r0);
-        tmem_ld32(tmem_row + col + 32, r1);
-        tmem_ld_wait();
-        const int boff = which == 0 ? B_SEM0 : B_COL0;
-        uint8_t* dst = which == 0 ? tP : tQ;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float v[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int n = 8 * j + q;
-            v[q] = fmaxf(__uint_as_float(n < 32 ? r0[n] : r1[n - 32]) + s_bias[boff + n], 0.f);
-          }
-          store_chunk(dst, 128 * 64 * 2, row, j, v);
-        }
-      }
-      fence_async_smem();
-      fence_before_sync();
-      named_bar_sync(bar_id, 128);
-      if (issue_warp) {
-        if (elect_one_sync()) {
-          fence_after_sync();
-          issue_gemm<K_SEMH, N_SEMH>(tmem_slot + C_R1, aP, wBase + OFF_W_SEMH);
-          issue_gemm<K_COL1, N_COL1>(tmem_slot + C_R0, aQ, wBase + OFF_W_COL1);
-          mma_commit(bar);
-        }
-        __syncwarp();
-      }
+      FNR_SLOT_WAIT()
+      epi32(tmem_row + C_R2 + 32 * half, tP, row, half, [&](int n, float x) { return fmaxf(x + s_bias[B_SEM0 + n], 0.f); });
+      epi32(tmem_row + C_R0 + 32 * half, tQ, row, half, [&](int n, float x) { return fmaxf(x + s_bias[B_COL0 + n], 0.f); });
+      FNR_SLOT_ISSUE(issue_gemm<K_SEMH, N_SEMH>(tmem_slot + C_R1, aP, wBase + OFF_W_SEMH);
+                     issue_gemm<K_COL1, N_COL1>(tmem_slot + C_R0, aQ, wBase + OFF_W_COL1))
 
       // ---- epilogue 4: logit ; c2 = relu(col1 + b) -> P --------------------------------------------
-      mbar_wait(bar, phase);
-      phase ^= 1;
-      fence_after_sync();
-      float logit;
-      {
+      FNR_SLOT_WAIT()
+      float logit = 0.f;
+      if (half == 0) {
         uint32_t lg[8];
         tmem_ld8(tmem_row + C_R1, lg);
-        uint32_t r0[32], r1[32];
-        tmem_ld32(tmem_row + C_R0, r0);
-        tmem_ld32(tmem_row + C_R0 + 32, r1);
         tmem_ld_wait();
         logit = __uint_as_float(lg[0]) + s_bias[B_SEMH];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float v[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int n = 8 * j + q;
-            v[q] = fmaxf(__uint_as_float(n < 32 ? r0[n] : r1[n - 32]) + s_bias[B_COL1 + n], 0.f);
-          }
-          store_chunk(tP, 128 * 64 * 2, row, j, v);
-        }
       }
-      fence_async_smem();
-      fence_before_sync();
-      named_bar_sync(bar_id, 128);
-      if (issue_warp) {
-        if (elect_one_sync()) {
-          fence_after_sync();
-          issue_gemm<K_COL2, N_COL2>(tmem_slot + C_R1, aP, wBase + OFF_W_COL2);
-          mma_commit(bar);
-        }
-        __syncwarp();
-      }
+      epi32(tmem_row + C_R0 + 32 * half, tP, row, half, [&](int n, float x) { return fmaxf(x + s_bias[B_COL1 + n], 0.f); });
+      FNR_SLOT_ISSUE(issue_gemm<K_COL2, N_COL2>(tmem_slot + C_R1, aP, wBase + OFF_W_COL2))
 
       // ---- epilogue 5: rgb = sigmoid(col2 + b) ; per-sample results to shared memory ---------------
-      mbar_wait(bar, phase);
-      phase ^= 1;
-      fence_after_sync();
-      {
+      FNR_SLOT_WAIT()
+      if (half == 0) {
         uint32_t c[8];
         tmem_ld8(tmem_row + C_R1, c);
         tmem_ld_wait();
@@ -418,6 +345,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
       }
       fence_before_sync();  // order this round's TMEM reads before the next round's MMAs
     }
+#undef FNR_SLOT_ISSUE
+#undef FNR_SLOT_WAIT
 
     // ---- per-group: write per-sample outputs, composite one ray per warp -------------------------
     __syncthreads();
@@ -516,8 +445,8 @@ int pick_rays_per_group(int S) {
   double best_waste = 2.0;
   for (int g = 1; g * S <= kMaxGroupPoints; ++g) {
     const int pts = g * S;
-    const int rounds = (pts + kCtaThreads - 1) / kCtaThreads;
-    const double waste = 1.0 - (double)pts / (rounds * kCtaThreads);
+    const int rounds = (pts + kSlots * 128 - 1) / (kSlots * 128);
+    const double waste = 1.0 - (double)pts / (rounds * kSlots * 128);
     if (waste < best_waste - 1e-9 || (waste < best_waste + 1e-9 && g > best)) {
       best_waste = waste;
       best = g;

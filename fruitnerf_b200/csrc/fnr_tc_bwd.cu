@@ -263,6 +263,34 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
   phase ^= 1;               \
   fence_after_sync();
 
+  // Deferred table-gradient scatter: tile i's 64 reds per thread are issued in four slices under tile i+1's
+  // first four MMA waits (they are fire-and-forget; issuing them in one burst only fills the LSU queue).
+  float pend_g[16];
+  Vec3 pend_pos = {0.f, 0.f, 0.f};
+  bool pend_valid = false;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) pend_g[i] = 0.f;
+  float2* const gtab = reinterpret_cast<float2*>(G.hash_table);
+  const bool do_scatter = !(a.debug_flags & 1);
+  auto scatter_slice = [&](int s0) {  // levels 8*half + 2*s0, +1
+    if (pend_valid && do_scatter) {
+#pragma unroll
+      for (int li = 2 * s0; li < 2 * s0 + 2; ++li) {
+        const int l = 8 * half + li;
+        const float g0 = pend_g[2 * li], g1 = pend_g[2 * li + 1];
+        if (g0 != 0.f || g1 != 0.f) {
+          const LevelCell c = level_cell(pend_pos, F.scalings[l]);
+          const uint32_t base = (uint32_t)l << F.log2T;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float w = corner_weight(c, k);
+            if (w != 0.f) atomicAdd(gtab + corner_row(c, k, hmask, base), make_float2(w * g0, w * g1));
+          }
+        }
+      }
+    }
+  };
+
 #pragma unroll 1
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const long long p = tile * 128 + row;
@@ -288,6 +316,7 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
       store_chunk(tA, 128 * 32 * 2, row, j, c);
     }
     FNR_SYNC_ISSUE(issue_gemm<32, 64>(tb + C_R0, aA, sb + OFF_W0))
+    scatter_slice(0);
 
     // ---- T1: colour-input chunks [sh | app] ; h1 -> H ; base1 ------------------------------------------
     int cam = 0;
@@ -317,6 +346,7 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
     FNR_WAIT()
     epi32(trow + C_R0 + 32 * half, tH, row, half, [&](int n, float x) { return fmaxf(x + sf[F_B0 + n], 0.f); });
     FNR_SYNC_ISSUE(issue_gemm<64, 16>(tb + C_R1, aH, sb + OFF_W1))
+    scatter_slice(1);
 
     // ---- T2: [h0 | geo] ; geo chunks ; dlogit tile ; semantic0 + colour0 --------------------------------
     FNR_WAIT()
@@ -346,6 +376,7 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
       }
     }
     FNR_SYNC_ISSUE(issue_gemm_lo<16, 64>(tb + C_R2, aGEO, aGEO + LO64, sb + OFF_WS0); issue_gemm<64, 64>(tb + C_R0, aCIN, sb + OFF_WC0))
+    scatter_slice(2);
 
     // ---- T3: z1 -> A, dz1 -> DY, c1 -> C1 ; colour1 + AV + AS0 ----------------------------------------
     FNR_WAIT()
@@ -370,6 +401,7 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
     epi32(trow + C_R0 + 32 * half, tC1, row, half, [&](int n, float x) { return fmaxf(x + sf[F_BC0 + n], 0.f); });
     FNR_SYNC_ISSUE(issue_gemm<64, 64>(tb + C_R0, aC1, sb + OFF_WC1); issue_dw<16>(tb + C_AV, aA, aA + LO64, aD16, aD16 + LO16, !first);
                    issue_dw<16>(tb + C_AS0, aDY, aDY + LO64, aGEO, aGEO + LO64, !first))
+    scatter_slice(3);
 
     // ---- T4: c2 -> A ; do3 -> D16 ; AC2 + dc2 -----------------------------------------------------------
     FNR_WAIT()
@@ -471,35 +503,24 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
     FNR_SYNC_ISSUE(issue_dw<32>(tb + C_AB0, aDY, aDY + LO64, aA, aA + LO32, !first); issue_dw<16>(tb + C_AB0B, aDY, aDY + LO64, aONES, 0u, !first);
                    issue_dx<64, 32>(tb + C_R2, aDY, sb + OFF_W0))
 
-    // ---- T9: denc -> hash-table gradient scatter (this thread: levels 8*half .. 8*half+7) ----------------
+    // ---- T9: denc (this thread: levels 8*half .. 8*half+7) -> deferred scatter state ----------------------
     FNR_WAIT()
     {
       uint32_t r0[16];
       tmem_ld16(trow + C_R2 + 16 * half, r0);
       tmem_ld_wait();
-      if (valid && !(a.debug_flags & 1)) {
-        float2* gt = reinterpret_cast<float2*>(G.hash_table);
 #pragma unroll
-        for (int li = 0; li < 8; ++li) {
-          const int l = 8 * half + li;
-          const float g0 = __uint_as_float(r0[2 * li]), g1 = __uint_as_float(r0[2 * li + 1]);
-          if (g0 != 0.f || g1 != 0.f) {
-            const LevelCell c = level_cell(pos, F.scalings[l]);
-            const uint32_t base = (uint32_t)l << F.log2T;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const float w = corner_weight(c, k);
-              if (w != 0.f) atomicAdd(gt + corner_row(c, k, hmask, base), make_float2(w * g0, w * g1));
-            }
-          }
-        }
-      }
+      for (int i = 0; i < 16; ++i) pend_g[i] = __uint_as_float(r0[i]);
+      pend_pos = pos;
+      pend_valid = valid;
     }
     fence_before_sync();  // this tile's TMEM reads are ordered before the next tile's MMAs (via the next barrier)
     first = false;
   }
 #undef FNR_SYNC_ISSUE
 #undef FNR_WAIT
+#pragma unroll
+  for (int s0 = 0; s0 < 4; ++s0) scatter_slice(s0);
 
   // ---- flush the resident accumulators ---------------------------------------------------------------
   fence_before_sync();

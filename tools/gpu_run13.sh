@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 300 > gpurun_out/pytest_sub.log 2>&1; echo "pytest rc=$?"; grep -E "AssertionError|^FAILED|passed|failed|Error" gpurun_out/pytest_sub.log | head
+for f in 0 1; do
+FNR_DEBUG_BWD=$f timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu 2>/dev/null | python -c "import sys,json; j=json.loads(sys.stdin.read()); print('flags $f', {k:round(j[k],3) for k in ('ms_per_step','fwd_ms','bwd_ms')}, int(j['value']), int(j['e2e']['value']))"
+done
