@@ -29,7 +29,9 @@ using namespace tcx;
 
 namespace {
 
-constexpr int kT = 256;  // threads per CTA: 2 threads per point (column halves), 8 warps
+constexpr int kTC = 256;  // compute threads: 2 threads per point (column halves), 8 warps
+constexpr int kTS = 128;  // scatter threads: 4 warps that only issue the hash-table gradient reds
+constexpr int kT = kTC + kTS;
 constexpr int GEO = 15, ENC = 32, H = 64, APP = 32, SHD = 16;
 
 // ---- shared-memory map (bytes) ------------------------------------------------------------------
@@ -53,6 +55,8 @@ constexpr int OFF_ONES = OFF_DY + TILE64;                  // [128][16] bf16, co
 constexpr int OFF_D16 = OFF_ONES + 128 * 16 * 2;           // 16-wide dY tile (hi 4 KB, lo 4 KB)
 constexpr int OFF_END = OFF_D16 + 2 * 128 * 16 * 2;
 constexpr int kSmem = OFF_END;
+// denc hand-off to the scatter warps lives in the C1 tile, which is idle between a tile's T6 and the next tile's T3
+constexpr int STAGE_STRIDE = 36;  // floats per row (32 denc + pos xyz + valid), padded: conflict-free 16-byte accesses
 constexpr int GEO_CHUNK = 6 * 2048;                        // byte offset of chunk 6 inside a K=64 tile half
 static_assert(kSmem + 64 <= 227 * 1024, "shared-memory budget");
 static_assert(OFF_H % 16 == 0 && OFF_D16 % 16 == 0, "tile alignment");
@@ -153,6 +157,15 @@ __device__ __forceinline__ void epi32_masked(uint32_t taddr32, const uint8_t* ac
   }
 }
 
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+constexpr int BAR_COMPUTE = 1, BAR_FULL = 2, BAR_EMPTY = 3;
+
 struct BwdArgs {
   KField F;
   KParams P;
@@ -170,8 +183,9 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
   __shared__ uint32_t s_tmem_base;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = tid & 127;   // point (TMEM lane) of this thread
-  const int half = tid >> 7;   // which 32 of 64 accumulator columns / which 8 of 16 levels this thread owns
+  const bool is_compute = tid < kTC;
+  const int row = tid & 127;          // point (TMEM lane) of this thread (compute) / point it scatters (scatter warps)
+  const int half = (tid >> 7) & 1;    // compute threads: which 32 of 64 accumulator columns this thread owns
   const KParams& P = a.P;
   const KParams& G = a.G;
   const KField& F = a.F;
@@ -209,7 +223,7 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
     }
     sf[i] = v;
   }
-  if (half == 0) {  // ONES tile: column 0 = 1 (bf16 0x3F80), everything else 0
+  if (tid < 128) {  // ONES tile: column 0 = 1 (bf16 0x3F80), everything else 0
     uint8_t* ones = smem + OFF_ONES;
     *reinterpret_cast<uint4*>(ones + row * 16) = make_uint4(0x00003F80u, 0u, 0u, 0u);
     *reinterpret_cast<uint4*>(ones + 2048 + row * 16) = make_uint4(0u, 0u, 0u, 0u);
@@ -249,7 +263,7 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
 #define FNR_SYNC_ISSUE(...)            \
   fence_async_smem();                  \
   fence_before_sync();                 \
-  __syncthreads();                     \
+  named_bar_sync(BAR_COMPUTE, kTC);    \
   if (warp == 0) {                     \
     if (elect_one_sync()) {            \
       fence_after_sync();              \
@@ -263,34 +277,93 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
   phase ^= 1;               \
   fence_after_sync();
 
-  // Deferred table-gradient scatter: tile i's 64 reds per thread are issued in four slices under tile i+1's
-  // first four MMA waits (they are fire-and-forget; issuing them in one burst only fills the LSU queue).
-  float pend_g[16];
-  Vec3 pend_pos = {0.f, 0.f, 0.f};
-  bool pend_valid = false;
+  float* stage = reinterpret_cast<float*>(tC1);  // [128][STAGE_STRIDE]: denc[32], pos xyz, valid (see STAGE_STRIDE)
+
+  if (!is_compute) {
+    // ================= scatter warps: hash-table gradient reds, decoupled from the tensor chain =================
+    reg_dec<72>();
+    float2* const gtab = reinterpret_cast<float2*>(G.hash_table);
+    const bool do_scatter = !(a.debug_flags & 1);
+    named_bar_arrive(BAR_EMPTY, kT);
+#pragma unroll 1
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      named_bar_sync(BAR_FULL, kT);
+      float g[32];
+      const float4* src = reinterpret_cast<const float4*>(stage + row * STAGE_STRIDE);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) pend_g[i] = 0.f;
-  float2* const gtab = reinterpret_cast<float2*>(G.hash_table);
-  const bool do_scatter = !(a.debug_flags & 1);
-  auto scatter_slice = [&](int s0) {  // levels 8*half + 2*s0, +1
-    if (pend_valid && do_scatter) {
+      for (int q = 0; q < 8; ++q) {
+        const float4 v = src[q];
+        g[4 * q] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w;
+      }
+      const float4 pv = src[8];
+      if (tile + gridDim.x < tiles) named_bar_arrive(BAR_EMPTY, kT);  // staging may be overwritten
+      const Vec3 pos = {pv.x, pv.y, pv.z};
+      const bool live = pv.w != 0.f;
+      if (do_scatter) {
+        // Levels 0..7: the 32 lanes of a warp are consecutive samples of a ray and share grid cells, so the
+        // contributions of a run of lanes in the same cell are summed with a segmented suffix scan and only
+        // the head lane of each run issues the 8 reds (run length ~25 at level 0, ~2.6 at level 7 on the
+        // bench workload).  The SM sustains only ~0.4 scattered 8-byte red lanes per cycle: fewer lanes = faster.
+#pragma unroll 1
+        for (int l = 0; l < 8; ++l) {
+          const LevelCell c = level_cell(pos, F.scalings[l]);
+          const uint32_t key = live ? (c.hx[0] ^ c.hy[0] ^ c.hz[0]) : (0x80000000u | (uint32_t)lane);
+          const uint32_t prev = __shfl_up_sync(kTcFullMask, key, 1);
+          const bool head = lane == 0 || prev != key;
+          // run = maximal stretch of CONSECUTIVE lanes with the same cell: [lane, run_end)
+          const uint32_t heads = __ballot_sync(kTcFullMask, head);
+          const uint32_t above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
+          const int run_end = above ? (__ffs(above) - 1) : 32;
+          bool same[5];
 #pragma unroll
-      for (int li = 2 * s0; li < 2 * s0 + 2; ++li) {
-        const int l = 8 * half + li;
-        const float g0 = pend_g[2 * li], g1 = pend_g[2 * li + 1];
-        if (g0 != 0.f || g1 != 0.f) {
-          const LevelCell c = level_cell(pend_pos, F.scalings[l]);
-          const uint32_t base = (uint32_t)l << F.log2T;
+          for (int q = 0; q < 5; ++q) same[q] = lane + (1 << q) < run_end;
+          const float g0 = live ? g[2 * l] : 0.f, g1 = live ? g[2 * l + 1] : 0.f;
+          float v0[8], v1[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const float w = corner_weight(c, k);
-            if (w != 0.f) atomicAdd(gtab + corner_row(c, k, hmask, base), make_float2(w * g0, w * g1));
+            v0[k] = w * g0;
+            v1[k] = w * g1;
+          }
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            const int dd = 1 << q;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float t0 = __shfl_down_sync(kTcFullMask, v0[k], dd), t1 = __shfl_down_sync(kTcFullMask, v1[k], dd);
+              if (same[q]) {
+                v0[k] += t0;
+                v1[k] += t1;
+              }
+            }
+          }
+          if (head && live) {
+            const uint32_t base = (uint32_t)l << F.log2T;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (v0[k] != 0.f || v1[k] != 0.f) atomicAdd(gtab + corner_row(c, k, hmask, base), make_float2(v0[k], v1[k]));
+          }
+        }
+        if (live) {
+#pragma unroll
+          for (int l = 8; l < 16; ++l) {
+            const float g0 = g[2 * l], g1 = g[2 * l + 1];
+            if (g0 != 0.f || g1 != 0.f) {
+              const LevelCell c = level_cell(pos, F.scalings[l]);
+              const uint32_t base = (uint32_t)l << F.log2T;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float w = corner_weight(c, k);
+                if (w != 0.f) atomicAdd(gtab + corner_row(c, k, hmask, base), make_float2(w * g0, w * g1));
+              }
+            }
           }
         }
       }
     }
-  };
-
+  } else {
+  // ================= compute warps: recompute + dX / dW chain on the tensor cores =================
+  reg_inc<216>();
 #pragma unroll 1
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const long long p = tile * 128 + row;
@@ -316,7 +389,6 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
       store_chunk(tA, 128 * 32 * 2, row, j, c);
     }
     FNR_SYNC_ISSUE(issue_gemm<32, 64>(tb + C_R0, aA, sb + OFF_W0))
-    scatter_slice(0);
 
     // ---- T1: colour-input chunks [sh | app] ; h1 -> H ; base1 ------------------------------------------
     int cam = 0;
@@ -346,7 +418,6 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
     FNR_WAIT()
     epi32(trow + C_R0 + 32 * half, tH, row, half, [&](int n, float x) { return fmaxf(x + sf[F_B0 + n], 0.f); });
     FNR_SYNC_ISSUE(issue_gemm<64, 16>(tb + C_R1, aH, sb + OFF_W1))
-    scatter_slice(1);
 
     // ---- T2: [h0 | geo] ; geo chunks ; dlogit tile ; semantic0 + colour0 --------------------------------
     FNR_WAIT()
@@ -376,7 +447,6 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
       }
     }
     FNR_SYNC_ISSUE(issue_gemm_lo<16, 64>(tb + C_R2, aGEO, aGEO + LO64, sb + OFF_WS0); issue_gemm<64, 64>(tb + C_R0, aCIN, sb + OFF_WC0))
-    scatter_slice(2);
 
     // ---- T3: z1 -> A, dz1 -> DY, c1 -> C1 ; colour1 + AV + AS0 ----------------------------------------
     FNR_WAIT()
@@ -398,10 +468,10 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
         store_chunk(tDY, 128 * 64 * 2, row, 4 * half + j, dz);
       }
     }
+    named_bar_sync(BAR_EMPTY, kT);  // the scatter warps have copied the previous tile's hand-off out of the C1 region
     epi32(trow + C_R0 + 32 * half, tC1, row, half, [&](int n, float x) { return fmaxf(x + sf[F_BC0 + n], 0.f); });
     FNR_SYNC_ISSUE(issue_gemm<64, 64>(tb + C_R0, aC1, sb + OFF_WC1); issue_dw<16>(tb + C_AV, aA, aA + LO64, aD16, aD16 + LO16, !first);
                    issue_dw<16>(tb + C_AS0, aDY, aDY + LO64, aGEO, aGEO + LO64, !first))
-    scatter_slice(3);
 
     // ---- T4: c2 -> A ; do3 -> D16 ; AC2 + dc2 -----------------------------------------------------------
     FNR_WAIT()
@@ -503,30 +573,32 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
     FNR_SYNC_ISSUE(issue_dw<32>(tb + C_AB0, aDY, aDY + LO64, aA, aA + LO32, !first); issue_dw<16>(tb + C_AB0B, aDY, aDY + LO64, aONES, 0u, !first);
                    issue_dx<64, 32>(tb + C_R2, aDY, sb + OFF_W0))
 
-    // ---- T9: denc (this thread: levels 8*half .. 8*half+7) -> deferred scatter state ----------------------
+    // ---- T9: denc -> hand-off to the scatter warps (C1 region is idle since T6) ------------------------------
     FNR_WAIT()
     {
       uint32_t r0[16];
       tmem_ld16(trow + C_R2 + 16 * half, r0);
       tmem_ld_wait();
+      float4* dst = reinterpret_cast<float4*>(stage + row * STAGE_STRIDE + 16 * half);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) pend_g[i] = __uint_as_float(r0[i]);
-      pend_pos = pos;
-      pend_valid = valid;
+      for (int q = 0; q < 4; ++q)
+        dst[q] = make_float4(__uint_as_float(r0[4 * q]), __uint_as_float(r0[4 * q + 1]), __uint_as_float(r0[4 * q + 2]), __uint_as_float(r0[4 * q + 3]));
+      if (half == 0) reinterpret_cast<float4*>(stage + row * STAGE_STRIDE + 32)[0] = make_float4(pos.x, pos.y, pos.z, valid ? 1.f : 0.f);
     }
+    named_bar_arrive(BAR_FULL, kT);
     fence_before_sync();  // this tile's TMEM reads are ordered before the next tile's MMAs (via the next barrier)
     first = false;
   }
 #undef FNR_SYNC_ISSUE
 #undef FNR_WAIT
-#pragma unroll
-  for (int s0 = 0; s0 < 4; ++s0) scatter_slice(s0);
+  }  // compute warps
 
   // ---- flush the resident accumulators ---------------------------------------------------------------
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  if (!first) {
+  const bool did_work = (long long)blockIdx.x < tiles;
+  if (did_work && is_compute) {
     // M=64 accumulators: row i lives in TMEM lane (i % 16) + 32 * (i / 16)  ->  owner threads: lane < 16,
     // i = 16 * (warp & 3) + lane; the two halves split the columns of every accumulator.
     const bool owner = lane < 16;
@@ -616,7 +688,7 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
     }
   }
   __syncthreads();
-  if (!first) {
+  if (did_work) {
     // folded semantic tail: logit = head_w . (W1 z1 + b1) + head_b, with v = sum dlogit * z1, s = sum dlogit
     const float* v = sf + F_RED;
     float sdl = 0.f;

@@ -32,13 +32,7 @@ __device__ __forceinline__ void stage_weight(uint8_t* tile, F getw) {
 __device__ __forceinline__ void store_chunk(uint8_t* tile_hi, int lo_off, int row, int j, const float (&v)[8]) {
   uint32_t h[4], l[4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float h0, l0, h1, l1;
-    split_bf16(v[2 * q], h0, l0);
-    split_bf16(v[2 * q + 1], h1, l1);
-    h[q] = pack_bf16x2(h0, h1);
-    l[q] = pack_bf16x2(l0, l1);
-  }
+  for (int q = 0; q < 4; ++q) split_pack_bf16x2(v[2 * q], v[2 * q + 1], h[q], l[q]);
   uint8_t* p = tile_hi + j * (128 * 16) + row * 16;
   *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
   *reinterpret_cast<uint4*>(p + lo_off) = make_uint4(l[0], l[1], l[2], l[3]);

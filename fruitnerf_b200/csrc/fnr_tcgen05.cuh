@@ -158,6 +158,13 @@ __device__ __forceinline__ void split_bf16(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
+// Packed split of two values: hi = {bf16(a), bf16(b)}, lo = {bf16(a - hi_a), bf16(b - hi_b)} (a in the low half).
+__device__ __forceinline__ void split_pack_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hb), "f"(a - ha));
+}
+
 // ---- fp16 hi/lo split -------------------------------------------------------------------------
 // x ~= hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 mantissa bits.  Conversions saturate to the
 // finite fp16 range (|x| <= 65504); values below the fp16 subnormal floor lose only absolute 3e-8.
