@@ -165,6 +165,7 @@ __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.al
 template <int N>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 constexpr int BAR_COMPUTE = 1, BAR_FULL = 2, BAR_EMPTY = 3;
+constexpr int kAggLevels = 4;  // coarse levels whose reds are run-length aggregated across the warp
 
 struct BwdArgs {
   KField F;
@@ -300,12 +301,12 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
       const Vec3 pos = {pv.x, pv.y, pv.z};
       const bool live = pv.w != 0.f;
       if (do_scatter) {
-        // Levels 0..7: the 32 lanes of a warp are consecutive samples of a ray and share grid cells, so the
+        // Levels 0..kAggLevels-1: the 32 lanes of a warp are consecutive samples of a ray and share grid cells, so the
         // contributions of a run of lanes in the same cell are summed with a segmented suffix scan and only
         // the head lane of each run issues the 8 reds (run length ~25 at level 0, ~2.6 at level 7 on the
         // bench workload).  The SM sustains only ~0.4 scattered 8-byte red lanes per cycle: fewer lanes = faster.
 #pragma unroll 1
-        for (int l = 0; l < 8; ++l) {
+        for (int l = 0; l < kAggLevels; ++l) {
           const LevelCell c = level_cell(pos, F.scalings[l]);
           const uint32_t key = live ? (c.hx[0] ^ c.hy[0] ^ c.hz[0]) : (0x80000000u | (uint32_t)lane);
           const uint32_t prev = __shfl_up_sync(kTcFullMask, key, 1);
@@ -346,15 +347,28 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
         }
         if (live) {
 #pragma unroll
-          for (int l = 8; l < 16; ++l) {
+          for (int l = kAggLevels; l < 16; ++l) {
             const float g0 = g[2 * l], g1 = g[2 * l + 1];
             if (g0 != 0.f || g1 != 0.f) {
               const LevelCell c = level_cell(pos, F.scalings[l]);
               const uint32_t base = (uint32_t)l << F.log2T;
+              // x-neighbours (floor x even, ceil = floor + 1) are adjacent table rows r, r^1: one 16-byte red
+              // instead of two 8-byte ones.  Corner pairs (x=floor, x=ceil) per (y,z): (6,5) (7,4) (2,1) (3,0).
+              const bool pair = ((c.hx[0] & 1u) == 0u) && (c.hx[1] == c.hx[0] + 1u);
+              constexpr int kf[4] = {6, 7, 2, 3}, kc[4] = {5, 4, 1, 0};
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const float w = corner_weight(c, k);
-                if (w != 0.f) atomicAdd(gtab + corner_row(c, k, hmask, base), make_float2(w * g0, w * g1));
+              for (int q = 0; q < 4; ++q) {
+                const float wf = corner_weight(c, kf[q]), wc = corner_weight(c, kc[q]);
+                const uint32_t rf = corner_row(c, kf[q], hmask, base);
+                if (pair) {
+                  const uint32_t r0 = rf & ~1u;
+                  const bool f_first = (rf & 1u) == 0u;
+                  const float4 v = f_first ? make_float4(wf * g0, wf * g1, wc * g0, wc * g1) : make_float4(wc * g0, wc * g1, wf * g0, wf * g1);
+                  atomicAdd(reinterpret_cast<float4*>(gtab + r0), v);
+                } else {
+                  if (wf != 0.f) atomicAdd(gtab + rf, make_float2(wf * g0, wf * g1));
+                  if (wc != 0.f) atomicAdd(gtab + corner_row(c, kc[q], hmask, base), make_float2(wc * g0, wc * g1));
+                }
               }
             }
           }
