@@ -231,9 +231,27 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
           const int l = 8 * half + li;
           const LevelCell c = level_cell(pos, F.scalings[l]);
           const uint32_t base = (uint32_t)l << F.log2T;
+          // x-neighbours (floor x even, ceil = floor + 1) are adjacent table rows r, r^1: one 16-byte load
+          // fetches both; only lanes with an odd floor x issue the second, 8-byte load.  Corner pairs
+          // (x = floor, x = ceil) per (y,z): (6,5) (7,4) (2,1) (3,0).  Fewer LDG instructions and fewer
+          // distinct lines per instruction = fewer L1TEX wavefront replays (the gather's bound).
+          const bool pair = ((c.hx[0] & 1u) == 0u) && (c.hx[1] == c.hx[0] + 1u);
+          constexpr int kf[4] = {6, 7, 2, 3}, kc[4] = {5, 4, 1, 0};
           float2 f[8];
+          float4 pv[4];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) f[k] = __ldg(table + corner_row(c, k, hmask, base));
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t rf = corner_row(c, kf[q], hmask, base);
+            pv[q] = __ldg(reinterpret_cast<const float4*>(table + (rf & ~1u)));
+            if (!pair) f[kc[q]] = __ldg(table + corner_row(c, kc[q], hmask, base));
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t rf = corner_row(c, kf[q], hmask, base);
+            const bool f_first = (rf & 1u) == 0u;
+            f[kf[q]] = f_first ? make_float2(pv[q].x, pv[q].y) : make_float2(pv[q].z, pv[q].w);
+            if (pair) f[kc[q]] = f_first ? make_float2(pv[q].z, pv[q].w) : make_float2(pv[q].x, pv[q].y);
+          }
           const float2 r = trilerp(f, c);
           enc[2 * li] = r.x;
           enc[2 * li + 1] = r.y;
