@@ -133,6 +133,21 @@ class ExportOut(C.Structure):
     ]
 
 
+class DensityDesc(C.Structure):
+    _fields_ = [
+        ("num_levels", C.c_int32),
+        ("log2_hashmap_size", C.c_int32),
+        ("hidden_dim", C.c_int32),
+        ("scalings", C.c_float * FNR_MAX_LEVELS),
+        ("aabb", C.c_float * 6),
+        ("position_mode", C.c_int32),
+    ]
+
+
+class DensityParams(C.Structure):
+    _fields_ = [("hash_table", C.c_void_p), ("w0", C.c_void_p), ("b0", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p)]
+
+
 LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libfruitnerf_b200.so"
 
 # every symbol include/fruitnerf_b200.h declares
@@ -144,6 +159,10 @@ EXPORTED_SYMBOLS = (
     "fnr_render_backward_scratch_bytes",
     "fnr_export_forward",
     "fnr_hash_indices",
+    "fnr_proposal_weights_forward",
+    "fnr_proposal_weights_backward",
+    "fnr_pdf_sample",
+    "fnr_interlevel_loss",
 )
 
 _lib = None
@@ -182,6 +201,17 @@ def load() -> C.CDLL:
     ]
     lib.fnr_hash_indices.restype = C.c_int
     lib.fnr_hash_indices.argtypes = [C.POINTER(FieldDesc), C.POINTER(RayBatch), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fnr_proposal_weights_forward.restype = C.c_int
+    lib.fnr_proposal_weights_forward.argtypes = [C.POINTER(DensityDesc), C.POINTER(DensityParams), C.POINTER(RayBatch), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fnr_proposal_weights_backward.restype = C.c_int
+    lib.fnr_proposal_weights_backward.argtypes = [C.POINTER(DensityDesc), C.POINTER(DensityParams), C.POINTER(RayBatch), C.c_void_p, C.c_void_p,
+                                                  C.c_void_p, C.POINTER(DensityParams), C.c_void_p]
+    lib.fnr_pdf_sample.restype = C.c_int
+    lib.fnr_pdf_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fnr_interlevel_loss.restype = C.c_int
+    lib.fnr_interlevel_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]
     if lib.fnr_version() != 1:
         raise FruitNerfNativeError(f"ABI version mismatch: library reports {lib.fnr_version()}")
     _lib = lib

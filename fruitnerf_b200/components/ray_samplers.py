@@ -41,7 +41,8 @@ class SpacedSampler(nn.Module):
             upper = torch.cat([centers, bins[..., -1:]], -1)
             lower = torch.cat([bins[..., :1], centers], -1)
             bins = lower + (upper - lower) * t_rand
-        return bins
+        # nerfstudio's TensorDataclass broadcasts every RaySamples field to the ray batch shape
+        return bins.expand(num_rays, num_samples + 1)
 
     def generate_ray_samples(self, ray_bundle: Optional[RayBundle] = None, num_samples: Optional[int] = None) -> RaySamples:
         assert ray_bundle is not None

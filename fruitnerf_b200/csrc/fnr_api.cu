@@ -341,4 +341,119 @@ int fnr_hash_indices(const fnr_field_desc* desc, const fnr_ray_batch* rays, int3
   return launch_hash_indices(make_field(desc), Rr, rows, positions, reinterpret_cast<cudaStream_t>(stream));
 }
 
+static int make_density(const fnr_density_desc* d, const fnr_density_params* p, KDensity* K, const char* what) {
+  if (!d || !p) {
+    set_error("%s: NULL density desc/params", what);
+    return FNR_ERR_INVALID_ARGUMENT;
+  }
+  int max_levels, hidden, max_bins;
+  proposal_limits(&max_levels, &hidden, &max_bins);
+  if (d->num_levels < 1 || d->num_levels > max_levels || d->hidden_dim != hidden || d->log2_hashmap_size < 1 || d->log2_hashmap_size > 26) {
+    set_error("unsupported proposal network (levels %d <= %d, hidden %d == %d)", d->num_levels, max_levels, d->hidden_dim, hidden);
+    return FNR_ERR_UNSUPPORTED;
+  }
+  if (!p->hash_table || !p->w0 || !p->b0 || !p->w1 || !p->b1) {
+    set_error("%s: NULL proposal parameter pointer", what);
+    return FNR_ERR_INVALID_ARGUMENT;
+  }
+  K->L = d->num_levels;
+  K->log2T = d->log2_hashmap_size;
+  K->position_mode = d->position_mode;
+  memcpy(K->scalings, d->scalings, sizeof(K->scalings));
+  memcpy(K->aabb, d->aabb, sizeof(K->aabb));
+  K->hash_table = p->hash_table;
+  K->w0 = p->w0;
+  K->b0 = p->b0;
+  K->w1 = p->w1;
+  K->b1 = p->b1;
+  return FNR_OK;
+}
+
+static int make_plain_rays(const fnr_ray_batch* r, KRays* K) {
+  if (!r || r->num_rays < 0 || r->num_samples < 1 || (r->num_rays > 0 && (!r->origins || !r->directions || !r->starts || !r->ends))) {
+    set_error("invalid ray batch");
+    return FNR_ERR_INVALID_ARGUMENT;
+  }
+  K->R = r->num_rays;
+  K->S = r->num_samples;
+  K->origins = r->origins;
+  K->directions = r->directions;
+  K->starts = r->starts;
+  K->ends = r->ends;
+  K->camera_indices = nullptr;
+  return FNR_OK;
+}
+
+int fnr_proposal_weights_forward(const fnr_density_desc* desc, const fnr_density_params* params, const fnr_ray_batch* rays, float* density,
+                                 float* weights, void* stream) {
+  KDensity D;
+  KRays Rr;
+  int rc;
+  if ((rc = make_density(desc, params, &D, "params"))) return rc;
+  if ((rc = make_plain_rays(rays, &Rr))) return rc;
+  if (!weights) {
+    set_error("weights is NULL");
+    return FNR_ERR_INVALID_ARGUMENT;
+  }
+  return launch_proposal_weights_forward(D, Rr, density, weights, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fnr_proposal_weights_backward(const fnr_density_desc* desc, const fnr_density_params* params, const fnr_ray_batch* rays,
+                                  const float* density, const float* weights, const float* d_weights, const fnr_density_params* grads,
+                                  void* stream) {
+  KDensity D, G;
+  KRays Rr;
+  int rc;
+  if ((rc = make_density(desc, params, &D, "params"))) return rc;
+  if ((rc = make_density(desc, grads, &G, "grads"))) return rc;
+  if ((rc = make_plain_rays(rays, &Rr))) return rc;
+  if (!density || !weights || !d_weights) {
+    set_error("density / weights / d_weights are required");
+    return FNR_ERR_INVALID_ARGUMENT;
+  }
+  if (Rr.S > 1024) {
+    set_error("proposal backward supports at most 1024 samples per ray (got %d)", Rr.S);
+    return FNR_ERR_UNSUPPORTED;
+  }
+  return launch_proposal_weights_backward(D, G, Rr, density, weights, d_weights, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fnr_pdf_sample(const float* weights, const float* existing_bins, int32_t num_rays, int32_t num_existing, int32_t num_samples,
+                   const float* u_base, const float* u_rand, int32_t u_stride, float anneal, float histogram_padding, const float* nears,
+                   const float* fars, float* new_bins, float* starts, float* ends, void* stream) {
+  int max_levels, hidden, max_bins;
+  proposal_limits(&max_levels, &hidden, &max_bins);
+  if (num_rays < 0 || num_existing < 1 || num_samples < 1 || num_existing > max_bins || num_samples > max_bins) {
+    set_error("pdf_sample: unsupported sizes (S=%d, num_samples=%d, max %d)", num_existing, num_samples, max_bins);
+    return FNR_ERR_UNSUPPORTED;
+  }
+  if (num_rays > 0 && (!weights || !existing_bins || !u_base || !nears || !fars || !new_bins || !starts || !ends)) {
+    set_error("pdf_sample: NULL argument");
+    return FNR_ERR_INVALID_ARGUMENT;
+  }
+  if (u_rand && u_stride != 1 && u_stride != num_samples + 1) {
+    set_error("pdf_sample: u_stride must be 1 or num_samples+1");
+    return FNR_ERR_INVALID_ARGUMENT;
+  }
+  KPdf A{num_rays, num_existing, num_samples, weights, existing_bins, u_base, u_rand, u_stride, anneal, histogram_padding, 1e-5f,
+         nears,    fars,         new_bins,    starts,  ends};
+  return launch_pdf_sample(A, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fnr_interlevel_loss(const float* c, const float* w, const float* cp, const float* wp, int32_t num_rays, int32_t sc, int32_t sp,
+                        float mult, float* loss, float* d_wp, void* stream) {
+  int max_levels, hidden, max_bins;
+  proposal_limits(&max_levels, &hidden, &max_bins);
+  if (num_rays < 0 || sc < 1 || sp < 1 || sp > max_bins) {
+    set_error("interlevel_loss: unsupported sizes");
+    return FNR_ERR_UNSUPPORTED;
+  }
+  if (num_rays > 0 && (!c || !w || !cp || !wp || !loss)) {
+    set_error("interlevel_loss: NULL argument");
+    return FNR_ERR_INVALID_ARGUMENT;
+  }
+  KInterlevel A{num_rays, sc, sp, c, w, cp, wp, num_rays > 0 ? mult / ((float)num_rays * (float)sc) : 0.f, loss, d_wp};
+  return launch_interlevel_loss(A, reinterpret_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

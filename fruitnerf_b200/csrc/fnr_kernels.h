@@ -97,6 +97,51 @@ struct KExport {
   int64_t* semantics_colormap;
 };
 
+// ---- proposal stage (fnr_proposal.cu) ----
+struct KDensity {  // nerfstudio HashMLPDensityField: hash grid (L levels, F=2) -> Linear(2L,16) -> ReLU -> Linear(16,1)
+  int L, log2T, position_mode;
+  float scalings[FNR_MAX_LEVELS];
+  float aabb[6];
+  float* hash_table;
+  float* w0;
+  float* b0;
+  float* w1;
+  float* b1;
+};
+
+struct KPdf {
+  int R, S, num_samples;
+  const float* weights;        // [R,S]
+  const float* existing_bins;  // [R,S+1] spacing bins of the previous level
+  const float* u_base;         // [num_samples+1] = linspace(0, 1 - 1/NB, NB) made by the host
+  const float* u_rand;         // NULL (bin centres) | [R*u_stride]
+  int u_stride;                // 1 = single jitter per ray, num_samples+1 = per bin
+  float anneal, hist_padding, eps;
+  const float* nears;          // [R]
+  const float* fars;           // [R]
+  float* new_bins;             // [R,num_samples+1]
+  float* starts;               // [R,num_samples]
+  float* ends;                 // [R,num_samples]
+};
+
+struct KInterlevel {
+  int R, Sc, Sp;
+  const float* c;   // [R,Sc+1] final-level spacing bins
+  const float* w;   // [R,Sc]   final-level weights
+  const float* cp;  // [R,Sp+1] proposal spacing bins
+  const float* wp;  // [R,Sp]   proposal weights
+  float scale;      // mult / (R * Sc)
+  float* loss;      // accumulated into (1 float)
+  float* d_wp;      // [R,Sp] or NULL
+};
+
+int launch_proposal_weights_forward(const KDensity& D, const KRays& Rr, float* density, float* weights, cudaStream_t st);
+int launch_proposal_weights_backward(const KDensity& D, const KDensity& G, const KRays& Rr, const float* density, const float* weights,
+                                     const float* d_weights, cudaStream_t st);
+int launch_pdf_sample(const KPdf& A, cudaStream_t st);
+int launch_interlevel_loss(const KInterlevel& A, cudaStream_t st);
+int proposal_limits(int* max_levels, int* hidden, int* max_bins);
+
 int sm_count();
 
 int launch_simt_field_forward(Family fam, const KField& F, const KParams& P, const KRays& Rr, const KFieldOut& O, cudaStream_t st);

@@ -373,9 +373,36 @@ __global__ void __launch_bounds__(kThreads) simt_composite_backward_kernel(KRays
       }
     }
     tot = warp_sum(tot);
+    // suffix sums sum_{k>i} G_k w_k: for S <= 1024 from per-chunk totals + a reverse scan inside the chunk (no
+    // "total - prefix" cancellation on long rays); longer rays keep the prefix formulation
+    const bool exact_suffix = S <= 1024;
+    float later_chunks = 0.f;
+    if (exact_suffix) {
+      float chunk_tot = 0.f;
+      for (int c0 = 0, ci = 0; c0 < S; c0 += 32, ++ci) {
+        const int i = c0 + lane;
+        float v = 0.f;
+        if (i < S) {
+          float G = gr * (B.sample_rgb[3 * (base + i)] - lr) + gg * (B.sample_rgb[3 * (base + i) + 1] - lg) +
+                    gb * (B.sample_rgb[3 * (base + i) + 2] - lb) + gacc;
+          if (B.d_weights) G += B.d_weights[base + i];
+          if (B.pass_semantic_gradients) G += gsem * B.sample_semantics[base + i];
+          v = G * B.weights[base + i];
+        }
+        const float t = warp_sum(v);
+        if (lane == ci) chunk_tot = t;
+      }
+      float rs = chunk_tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_down_sync(kFull, rs, o);
+        if (lane + o < 32) rs += t;
+      }
+      later_chunks = rs - chunk_tot;
+    }
     // pass 2
     float run_x = 0.f, run_gw = 0.f;
-    for (int c0 = 0; c0 < S; c0 += 32) {
+    for (int c0 = 0, ci = 0; c0 < S; c0 += 32, ++ci) {
       const int i = c0 + lane;
       const bool in = i < S;
       float x = 0.f, G = 0.f, w = 0.f, delta = 0.f;
@@ -389,10 +416,18 @@ __global__ void __launch_bounds__(kThreads) simt_composite_backward_kernel(KRays
         if (B.pass_semantic_gradients) G += gsem * B.sample_semantics[base + i];
       }
       const float xin = warp_incl_scan(x, lane);
-      const float gwin = warp_incl_scan(G * w, lane);
+      const float gwv = G * w;
+      const float gwin = warp_incl_scan(gwv, lane);
+      float rsfx = gwv;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_down_sync(kFull, rsfx, o);
+        if (lane + o < 32) rsfx += t;
+      }
+      const float later = __shfl_sync(kFull, later_chunks, ci & 31);
       if (in) {
         const float Tnext = expf(-(run_x + xin));
-        const float suffix = tot - (run_gw + gwin);
+        const float suffix = exact_suffix ? (rsfx - gwv) + later : tot - (run_gw + gwin);
         float dsig = delta * (G * Tnext - suffix);
         if (B.d_sample_density) dsig += B.d_sample_density[base + i];
         float dr = w * gr, dg = w * gg, db = w * gb;

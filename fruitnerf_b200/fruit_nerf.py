@@ -19,6 +19,8 @@ from . import _lib as L
 from . import ops
 from .compat import FieldHeadNames, InstantiateConfig, RayBundle, RaySamples, SceneBox, Semantics
 from .components.ray_samplers import UniformLinDispPiecewiseSampler, UniformSamplerWithNoise
+from .components.proposal_sampler import ProposalNetworkSampler
+from .density_field import HashMLPDensityField
 from .fruit_field import FruitField, SceneContraction
 
 
@@ -71,6 +73,21 @@ class FruitNerfModelConfig(InstantiateConfig):
     implementation: Literal["tcnn", "torch", "b200"] = "b200"
 
 
+def _sdist(ray_samples: RaySamples) -> Tensor:
+    """nerfstudio ray_samples_to_sdist: [R, S+1] spacing bins."""
+    return torch.cat([ray_samples.spacing_starts[..., 0], ray_samples.spacing_ends[..., -1:, 0]], dim=-1)
+
+
+def _median_depth(weights: Tensor, ray_samples: RaySamples) -> Tensor:
+    """nerfstudio DepthRenderer(method="median") for the proposal levels (visualisation outputs)."""
+    with torch.no_grad():
+        steps = (ray_samples.frustums.starts + ray_samples.frustums.ends) / 2
+        cum = torch.cumsum(weights[..., 0], dim=-1)
+        split = torch.ones((*weights.shape[:-2], 1), device=weights.device) * 0.5
+        idx = torch.clamp(torch.searchsorted(cum, split, side="left"), 0, steps.shape[-2] - 1)
+        return torch.gather(steps[..., 0], dim=-1, index=idx)
+
+
 class FruitModel(nn.Module):
     """FruitModel based on the Nerfacto model (fruit_nerf.py:62-458)."""
 
@@ -115,17 +132,40 @@ class FruitModel(nn.Module):
             num_semantic_classes=1,
             pass_semantic_gradients=cfg.pass_semantic_gradients,
         )
-        # Proposal networks (fruit_nerf.py:104-158): the proposal stage is SURVEY.md 8(f) rank 1
-        # ("next").  Until its kernels land the sampler is nerfstudio's ProposalNetworkSampler with
-        # zero proposal iterations, i.e. its initial UniformLinDispPiecewiseSampler drawing the
-        # final num_nerf_samples_per_ray bins; weights_list / ray_samples_list then hold only the
-        # final level, exactly as nerfstudio returns them for num_proposal_network_iterations = 0.
-        self.proposal_networks = nn.ModuleList()
+        # Proposal networks + sampler (fruit_nerf.py:104-158)
         self.density_fns = []
-        self.proposal_sampler = UniformLinDispPiecewiseSampler(
-            num_samples=cfg.num_nerf_samples_per_ray, single_jitter=cfg.use_single_jitter
-        )
-        self.num_proposal_iterations_active = 0
+        num_prop_nets = cfg.num_proposal_iterations
+        self.proposal_networks = nn.ModuleList()
+        if cfg.use_same_proposal_network:
+            assert len(cfg.proposal_net_args_list) == 1, "Only one proposal network is allowed."
+            prop_net_args = {k: v for k, v in cfg.proposal_net_args_list[0].items()}
+            network = HashMLPDensityField(self.scene_box.aabb, spatial_distortion=scene_contraction, **prop_net_args)
+            self.proposal_networks.append(network)
+            self.density_fns.extend([network.density_fn for _ in range(num_prop_nets)])
+        else:
+            for i in range(num_prop_nets):
+                prop_net_args = cfg.proposal_net_args_list[min(i, len(cfg.proposal_net_args_list) - 1)]
+                network = HashMLPDensityField(self.scene_box.aabb, spatial_distortion=scene_contraction, **prop_net_args)
+                self.proposal_networks.append(network)
+            self.density_fns.extend([network.density_fn for network in self.proposal_networks])
+
+        def update_schedule(step):
+            return np.clip(np.interp(step, [0, cfg.proposal_warmup], [0, cfg.proposal_update_every]), 1, cfg.proposal_update_every)
+
+        if cfg.proposal_initial_sampler == "uniform":
+            # upstream leaves self.proposal_sampler unset on this branch (fruit_nerf.py:145-149): reject instead of crashing later
+            raise NotImplementedError('proposal_initial_sampler="uniform" builds no sampler in the reference either')
+        if num_prop_nets >= 1:
+            self.proposal_sampler = ProposalNetworkSampler(
+                num_nerf_samples_per_ray=cfg.num_nerf_samples_per_ray,
+                num_proposal_samples_per_ray=cfg.num_proposal_samples_per_ray,
+                num_proposal_network_iterations=cfg.num_proposal_iterations,
+                single_jitter=cfg.use_single_jitter,
+                update_sched=update_schedule,
+                initial_sampler=None,
+            )
+        else:  # nerfstudio with zero proposal iterations: the initial sampler draws the final bins
+            self.proposal_sampler = UniformLinDispPiecewiseSampler(num_samples=cfg.num_nerf_samples_per_ray, single_jitter=cfg.use_single_jitter)
         self.near_plane, self.far_plane = cfg.near_plane, cfg.far_plane
         self.rgb_loss = nn.MSELoss()
         self.binary_cross_entropy_loss = nn.BCEWithLogitsLoss(reduction="mean")
@@ -166,8 +206,10 @@ class FruitModel(nn.Module):
 
     def get_outputs(self, ray_bundle: RayBundle):
         """fruit_nerf.py:316-357 (and 272-314 for test_mode == 'inference')."""
-        ray_samples = self.proposal_sampler(ray_bundle)
-        weights_list, ray_samples_list = [], []
+        if isinstance(self.proposal_sampler, ProposalNetworkSampler):
+            ray_samples, weights_list, ray_samples_list = self.proposal_sampler(ray_bundle, density_fns=self.density_fns)
+        else:
+            ray_samples, weights_list, ray_samples_list = self.proposal_sampler(ray_bundle), [], []
         out = self._render(ray_samples)
         R = out["rgb"].shape[0]
         weights = out["weights"].unsqueeze(-1)
@@ -180,6 +222,8 @@ class FruitModel(nn.Module):
             "weights_list": weights_list,
             "ray_samples_list": ray_samples_list,
         }
+        for i in range(len(weights_list) - 1):  # prop_depth_i: median depth of each proposal level (fruit_nerf.py:339-340)
+            outputs[f"prop_depth_{i}"] = _median_depth(weights_list[i], ray_samples_list[i])
         outputs["semantics"] = out["semantics"].view(R, 1)
         semantic_labels = torch.sigmoid(outputs["semantics"].detach())
         threshold = 0.9
@@ -215,8 +259,7 @@ class FruitModel(nn.Module):
         return self.get_outputs(ray_bundle)
 
     def get_loss_dict(self, outputs, batch, metrics_dict=None):
-        """fruit_nerf.py:359-372.  interlevel_loss needs proposal levels; with zero proposal
-        iterations nerfstudio's interlevel_loss sums over no levels, i.e. 0."""
+        """fruit_nerf.py:359-372."""
         loss_dict = {}
         image = batch["image"].to(self.device)
         loss_dict["rgb_loss"] = self.rgb_loss(image, outputs["rgb"])
@@ -224,14 +267,38 @@ class FruitModel(nn.Module):
             outputs["semantics"], batch["fruit_mask"].to(self.device)
         )
         if self.training:
-            loss_dict["interlevel_loss"] = self.config.interlevel_loss_mult * torch.zeros((), device=self.device)
+            loss_dict["interlevel_loss"] = ops.interlevel_loss(
+                [w[..., 0] for w in outputs["weights_list"]], [_sdist(rs) for rs in outputs["ray_samples_list"]], self.config.interlevel_loss_mult
+            )
         return loss_dict
 
     def get_metrics_dict(self, outputs, batch):
         """fruit_nerf.py:396-401: PSNR (data_range 1)."""
         image = batch["image"].to(self.device)
         mse = torch.mean((outputs["rgb"].detach() - image) ** 2)
-        return {"psnr": -10.0 * torch.log10(mse)}
+        metrics = {"psnr": -10.0 * torch.log10(mse)}
+        with torch.no_grad():  # nerfstudio distortion_loss on the final level: a logged metric only (fruit_nerf.py:400)
+            t, w = _sdist(outputs["ray_samples_list"][-1]), outputs["weights_list"][-1][..., 0]
+            ut = (t[..., 1:] + t[..., :-1]) / 2
+            inter = torch.sum(w * torch.sum(w[..., None, :] * torch.abs(ut[..., :, None] - ut[..., None, :]), dim=-1), dim=-1)
+            intra = torch.sum(w**2 * (t[..., 1:] - t[..., :-1]), dim=-1) / 3
+            metrics["distortion"] = torch.mean(inter + intra)
+        return metrics
+
+    def get_training_callbacks(self, training_callback_attributes=None) -> List[Dict]:
+        """fruit_nerf.py:191-223: anneal the proposal weights before each iteration, count steps after."""
+        callbacks = []
+        if self.config.use_proposal_weight_anneal and isinstance(self.proposal_sampler, ProposalNetworkSampler):
+            N = self.config.proposal_weights_anneal_max_num_iters
+
+            def set_anneal(step):
+                train_frac = np.clip(step / N, 0, 1)
+                b = self.config.proposal_weights_anneal_slope
+                self.proposal_sampler.set_anneal(b * train_frac / ((b - 1) * train_frac + 1))
+
+            callbacks.append({"where_to_run": "BEFORE_TRAIN_ITERATION", "update_every_num_iters": 1, "func": set_anneal})
+            callbacks.append({"where_to_run": "AFTER_TRAIN_ITERATION", "update_every_num_iters": 1, "func": self.proposal_sampler.step_cb})
+        return callbacks
 
     @torch.no_grad()
     def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle: RayBundle) -> Dict[str, torch.Tensor]:

@@ -302,3 +302,132 @@ def export_batch(shape: FieldShape, params: Sequence[Tensor], origins: Tensor, n
                                float(far), B, S, int(point_base), C.byref(xp), C.byref(out), _stream(dev))
     )
     return dense
+
+
+# ======================================================================================================
+# Proposal-sampling stage (fruit_nerf/fruit_nerf.py:104-158, 318)
+# ======================================================================================================
+@dataclass
+class DensityShape:
+    """Static shape of a nerfstudio HashMLPDensityField as the kernels see it."""
+
+    num_levels: int
+    log2_hashmap_size: int
+    hidden_dim: int
+    scalings: Sequence[float]
+    aabb: Sequence[float]
+
+    def desc(self, position_mode: int) -> L.DensityDesc:
+        cache = self.__dict__.setdefault("_desc_cache", {})
+        if position_mode not in cache:
+            d = L.DensityDesc()
+            d.num_levels, d.log2_hashmap_size, d.hidden_dim = self.num_levels, self.log2_hashmap_size, self.hidden_dim
+            for i, v in enumerate(self.scalings):
+                d.scalings[i] = float(v)
+            for i, v in enumerate(self.aabb):
+                d.aabb[i] = float(v)
+            d.position_mode = position_mode
+            cache[position_mode] = d
+        return cache[position_mode]
+
+
+def _density_params(tensors: Sequence[Tensor]) -> L.DensityParams:
+    p = L.DensityParams()
+    p.hash_table, p.w0, p.b0, p.w1, p.b1 = [t.data_ptr() for t in tensors]
+    return p
+
+
+class _ProposalWeights(torch.autograd.Function):
+    """HashMLPDensityField.density_fn(frustum midpoints) + RaySamples.get_weights, fused."""
+
+    @staticmethod
+    def forward(ctx, shape: DensityShape, position_mode: int, origins, directions, starts, ends, *params):
+        dev = _require_cuda(origins, directions, starts, ends, *params)
+        lib = L.load()
+        R, S = starts.shape
+        origins, directions, starts, ends = map(_f32c, (origins, directions, starts, ends))
+        params = [p.detach() for p in params]
+        density = torch.empty((R, S), dtype=torch.float32, device=dev)
+        weights = torch.empty((R, S), dtype=torch.float32, device=dev)
+        rays = L.RayBatch(R, S, _ptr(origins), _ptr(directions), _ptr(starts), _ptr(ends), None)
+        desc = shape.desc(position_mode)
+        L.check(lib.fnr_proposal_weights_forward(C.byref(desc), C.byref(_density_params(params)), C.byref(rays), density.data_ptr(),
+                                                 weights.data_ptr(), _stream(dev)))
+        ctx.shape, ctx.position_mode = shape, position_mode
+        ctx.saved = (origins, directions, starts, ends, params, density, weights)
+        return weights
+
+    @staticmethod
+    def backward(ctx, g_w):
+        lib = L.load()
+        origins, directions, starts, ends, params, density, weights = ctx.saved
+        dev = density.device
+        R, S = starts.shape
+        flat, views = flat_zero_grads(params)
+        rays = L.RayBatch(R, S, _ptr(origins), _ptr(directions), _ptr(starts), _ptr(ends), None)
+        desc = ctx.shape.desc(ctx.position_mode)
+        L.check(lib.fnr_proposal_weights_backward(C.byref(desc), C.byref(_density_params(params)), C.byref(rays), density.data_ptr(),
+                                                  weights.data_ptr(), _f32c(g_w).data_ptr(), C.byref(_density_params(views)), _stream(dev)))
+        return (None, None, None, None, None, None, *views)
+
+
+def proposal_weights(shape: DensityShape, params: Sequence[Tensor], origins, directions, starts, ends, position_mode: int) -> Tensor:
+    """weights [R,S] of one proposal level."""
+    return _ProposalWeights.apply(shape, position_mode, origins, directions, starts, ends, *params)
+
+
+def pdf_sample(weights: Tensor, existing_bins: Tensor, num_samples: int, u_rand: Optional[Tensor], anneal: float, nears: Tensor, fars: Tensor,
+               histogram_padding: float = 0.01):
+    """PDFSampler + spacing->euclidean map.  Returns (new spacing bins [R,n+1], starts [R,n], ends [R,n]); no gradient
+    flows through the sampler (the reference detaches the bins)."""
+    dev = _require_cuda(weights, existing_bins, nears, fars)
+    lib = L.load()
+    R, S = weights.shape
+    weights, existing_bins = _f32c(weights.detach()), _f32c(existing_bins.detach())
+    nears, fars = _f32c(nears.reshape(-1)), _f32c(fars.reshape(-1))
+    nb = num_samples + 1
+    # as the reference: torch.linspace on the device the cdf lives on
+    u_base = torch.linspace(0.0, 1.0 - (1.0 / nb), steps=nb, device=dev)
+    stride = 0
+    if u_rand is not None:
+        u_rand = _f32c(u_rand)
+        stride = 1 if u_rand.numel() == R else nb
+    bins = torch.empty((R, nb), dtype=torch.float32, device=dev)
+    starts = torch.empty((R, num_samples), dtype=torch.float32, device=dev)
+    ends = torch.empty((R, num_samples), dtype=torch.float32, device=dev)
+    L.check(lib.fnr_pdf_sample(weights.data_ptr(), existing_bins.data_ptr(), R, S, num_samples, u_base.data_ptr(), _ptr(u_rand), stride,
+                               float(anneal), float(histogram_padding), nears.data_ptr(), fars.data_ptr(), bins.data_ptr(),
+                               starts.data_ptr(), ends.data_ptr(), _stream(dev)))
+    return bins, starts, ends
+
+
+class _InterlevelLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, c, w, cp, wp, mult: float):
+        dev = _require_cuda(c, w, cp, wp)
+        lib = L.load()
+        R, Sc = w.shape
+        Sp = wp.shape[1]
+        c, w, cp, wpc = map(_f32c, (c.detach(), w.detach(), cp.detach(), wp.detach()))
+        loss = torch.zeros((), dtype=torch.float32, device=dev)
+        d_wp = torch.empty((R, Sp), dtype=torch.float32, device=dev) if ctx.needs_input_grad[3] else None
+        L.check(lib.fnr_interlevel_loss(c.data_ptr(), w.data_ptr(), cp.data_ptr(), wpc.data_ptr(), R, Sc, Sp, float(mult), loss.data_ptr(),
+                                        _ptr(d_wp), _stream(dev)))
+        ctx.d_wp = d_wp
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, None, None, (ctx.d_wp * g if ctx.d_wp is not None else None), None
+
+
+def interlevel_loss(weights_list: Sequence[Tensor], sdist_list: Sequence[Tensor], mult: float = 1.0) -> Tensor:
+    """nerfstudio losses.interlevel_loss: weights_list[i] [R,S_i], sdist_list[i] [R,S_i+1]; the last entry is the final level."""
+    c, w = sdist_list[-1], weights_list[-1]
+    total = None
+    for sdist, wp in zip(sdist_list[:-1], weights_list[:-1]):
+        term = _InterlevelLoss.apply(c, w, sdist, wp, mult)
+        total = term if total is None else total + term
+    if total is None:
+        total = torch.zeros((), dtype=torch.float32, device=w.device)
+    return total

@@ -101,3 +101,17 @@ def targets(R: int, salt: int = 0, device="cpu") -> Tuple[Tensor, Tensor]:
     img = (hash_uniform(R * 3, 53 + salt, device).view(R, 3) + 1.0) * 0.5
     mask = ((hash_uniform(R, 59 + salt, device).view(R, 1) + 1.0) * 0.5 < 0.1).to(torch.float32)
     return img, mask
+
+
+def density_state(num_levels: int = 5, log2_hashmap_size: int = 17, hidden: int = 16, table_scale: float = 0.5, weight_gain: float = 1.5,
+                  salt: int = 5000, aabb=((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0)), device="cpu") -> Dict[str, Tensor]:
+    """State dict (nerfstudio torch-path key names) of a HashMLPDensityField proposal network, hash-generated."""
+    rows = num_levels * 2**log2_hashmap_size
+    sd = {"encoding.hash_table": (hash_uniform(rows * 2, salt + 1, device) * table_scale).view(rows, 2)}
+    k0, k1 = weight_gain / math.sqrt(2 * num_levels), weight_gain / math.sqrt(hidden)
+    sd["mlp_base.1.layers.0.weight"] = (hash_uniform(hidden * 2 * num_levels, salt + 2, device) * k0).view(hidden, 2 * num_levels)
+    sd["mlp_base.1.layers.0.bias"] = hash_uniform(hidden, salt + 3, device) * k0
+    sd["mlp_base.1.layers.1.weight"] = (hash_uniform(hidden, salt + 4, device) * k1).view(1, hidden)
+    sd["mlp_base.1.layers.1.bias"] = hash_uniform(1, salt + 5, device) * k1
+    sd["aabb"] = torch.tensor(aabb, dtype=torch.float32, device=device)
+    return sd

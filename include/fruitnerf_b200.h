@@ -173,6 +173,52 @@ typedef struct fnr_export_out {
   int64_t* semantics_colormap;       /* [B,S] label in {0,1} */
 } fnr_export_out;
 
+/* ---- proposal-sampling stage (nerfstudio ProposalNetworkSampler as FruitModel builds it,
+ * fruit_nerf/fruit_nerf.py:104-158, 318) ---- */
+
+/* HashMLPDensityField: hash grid (num_levels, F=2, 2^log2_hashmap_size rows per level) ->
+ * Linear(2*num_levels, 16) -> ReLU -> Linear(16, 1) -> trunc_exp * selector. */
+typedef struct fnr_density_desc {
+  int32_t num_levels;                /* <= 8 */
+  int32_t log2_hashmap_size;
+  int32_t hidden_dim;                /* 16 (proposal_net_args_list of all shipped configs) */
+  float scalings[FNR_MAX_LEVELS];
+  float aabb[6];
+  int32_t position_mode;             /* FNR_POS_* */
+} fnr_density_desc;
+
+typedef struct fnr_density_params {  /* fp32 device pointers, torch layouts; also used for gradients */
+  float* hash_table;                 /* [num_levels * 2^T, 2] */
+  float* w0;                         /* [16][2*num_levels] */
+  float* b0;                         /* [16] */
+  float* w1;                         /* [1][16] */
+  float* b1;                         /* [1] */
+} fnr_density_params;
+
+/* density_fn(frustum midpoints) + RaySamples.get_weights, fused: density [R,S] (may be NULL), weights [R,S]. */
+int fnr_proposal_weights_forward(const fnr_density_desc* desc, const fnr_density_params* params, const fnr_ray_batch* rays,
+                                 float* density, float* weights, void* stream);
+/* d_weights [R,S] -> gradients of the proposal network (accumulated into `grads`). */
+int fnr_proposal_weights_backward(const fnr_density_desc* desc, const fnr_density_params* params, const fnr_ray_batch* rays,
+                                  const float* density, const float* weights, const float* d_weights,
+                                  const fnr_density_params* grads, void* stream);
+
+/* PDFSampler.generate_ray_samples (include_original = False) followed by the piecewise
+ * linear-in-disparity spacing -> euclidean map of UniformLinDispPiecewiseSampler.
+ *   weights [R,S], existing_bins [R,S+1] (spacing space), u_base [num_samples+1] = linspace(0, 1-1/NB, NB)
+ *   (made by the caller, as the reference does with torch.linspace), u_rand NULL (bin centres, eval) or
+ *   [R*u_stride] uniform draws (u_stride 1 = single jitter, num_samples+1 = per bin), weights are raised to
+ *   `anneal` first.  Outputs: new_bins [R,num_samples+1] (spacing), starts/ends [R,num_samples] (euclidean). */
+int fnr_pdf_sample(const float* weights, const float* existing_bins, int32_t num_rays, int32_t num_existing,
+                   int32_t num_samples, const float* u_base, const float* u_rand, int32_t u_stride, float anneal,
+                   float histogram_padding, const float* nears, const float* fars, float* new_bins, float* starts,
+                   float* ends, void* stream);
+
+/* losses.interlevel_loss for ONE proposal level: adds mult * mean(lossfun_outer(c, w, cp, wp)) to *loss and
+ * writes d loss / d wp into d_wp [R,Sp] (may be NULL).  c [R,Sc+1], w [R,Sc] are the (detached) final level. */
+int fnr_interlevel_loss(const float* c, const float* w, const float* cp, const float* wp, int32_t num_rays, int32_t sc,
+                        int32_t sp, float mult, float* loss, float* d_wp, void* stream);
+
 int fnr_version(void);
 const char* fnr_last_error(void);
 

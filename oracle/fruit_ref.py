@@ -203,3 +203,53 @@ def export_select(out: Dict[str, Tensor]) -> Dict[str, Dict[str, Tensor]]:
     ):
         res[name] = {"points": pts[m], "colors": torch.hstack([rgb[m], torch.sigmoid(fourth[m]).unsqueeze(-1)])}
     return res
+
+
+# --------------------------------------------------------------------------------------------------
+# Proposal stage (fruit_nerf.py:104-158, 318): nerfstudio ProposalNetworkSampler on plain tensors
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class DensitySpec:
+    """proposal_net_args_list entry (fruit_nerf.py:121-127) of a HashMLPDensityField."""
+
+    num_levels: int = 5
+    max_res: int = 128
+    log2_hashmap_size: int = 17
+    base_res: int = 16
+    hidden_dim: int = 16
+
+    def scalings(self) -> Tensor:
+        return ns.hash_scalings(self.num_levels, self.base_res, self.max_res)
+
+
+def proposal_weights(pp: Dict[str, Tensor], spec: DensitySpec, origins, directions, starts, ends, aabb, contraction: bool = True) -> Tensor:
+    """density_fn(frustum midpoints) -> get_weights for one level.  starts/ends [R,S] -> weights [R,S]."""
+    pos = ns.frustum_positions(origins[:, None, :], directions[:, None, :], starts[..., None], ends[..., None])
+    dens = ns.proposal_density(pos, pp["encoding.hash_table"], spec.scalings(), spec.log2_hashmap_size, pp["mlp_base.1.layers.0.weight"],
+                               pp["mlp_base.1.layers.0.bias"], pp["mlp_base.1.layers.1.weight"], pp["mlp_base.1.layers.1.bias"], aabb, contraction)
+    return ns.get_weights((ends - starts)[..., None], dens)[..., 0]
+
+
+def proposal_sampler(prop_params, prop_specs, origins, directions, nears, fars, num_prop_samples, num_nerf_samples, aabb, t_rand0=None,
+                     u_rands=None, anneal: float = 1.0):
+    """ProposalNetworkSampler.generate_ray_samples.  ``t_rand0``: jitter of the initial sampler (None = eval);
+    ``u_rands``: list of PDF draws per PDF level (None = eval).  Returns (starts, ends, final_bins, weights_list, sdist_list)
+    where the lists cover the proposal levels only."""
+    R = origins.shape[0]
+    n = len(prop_params)
+    weights_list, sdist_list = [], []
+    bins = ns.spaced_bins(R, num_prop_samples[0], t_rand0)
+    weights = None
+    for lvl in range(n + 1):
+        is_prop = lvl < n
+        if lvl > 0:
+            ns_ = num_prop_samples[lvl] if is_prop else num_nerf_samples
+            u = None if u_rands is None else u_rands[lvl - 1]
+            bins = ns.pdf_sample(torch.pow(weights, anneal), bins, ns_, u)
+        e = ns.spacing_to_euclidean(bins, nears, fars)
+        starts, ends = e[:, :-1], e[:, 1:]
+        if is_prop:
+            weights = proposal_weights(prop_params[lvl], prop_specs[lvl], origins, directions, starts, ends, aabb)
+            weights_list.append(weights)
+            sdist_list.append(bins)
+    return starts, ends, bins, weights_list, sdist_list

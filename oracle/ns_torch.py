@@ -291,3 +291,126 @@ def rgb_mse(image: Tensor, rgb: Tensor) -> Tensor:
 
 def semantic_bce(logits: Tensor, mask: Tensor) -> Tensor:
     return torch.nn.functional.binary_cross_entropy_with_logits(logits, mask, reduction="mean")
+
+
+# --------------------------------------------------------------------------------------
+# Proposal stage                (fruit_nerf.py:104-158, 318; SURVEY.md section 8a row A13)
+# --------------------------------------------------------------------------------------
+def lindisp_piecewise_fn(x: Tensor) -> Tensor:
+    """[NS] UniformLinDispPiecewiseSampler spacing_fn: x/2 below 1, 1 - 1/(2x) above."""
+    return torch.where(x < 1, x / 2, 1 - 1 / (2 * x))
+
+
+def lindisp_piecewise_inv(x: Tensor) -> Tensor:
+    """[NS] UniformLinDispPiecewiseSampler spacing_fn_inv."""
+    return torch.where(x < 0.5, 2 * x, 1 / (2 - 2 * x))
+
+
+def spaced_bins(num_rays: int, num_samples: int, t_rand: Optional[Tensor]) -> Tensor:
+    """[NS] SpacedSampler.generate_ray_samples bins in spacing space.  ``t_rand`` [R,1] (single
+    jitter) or [R,S+1], or None for the deterministic (eval) bins."""
+    bins = torch.linspace(0.0, 1.0, num_samples + 1)[None, ...]
+    if t_rand is not None:
+        centers = (bins[..., 1:] + bins[..., :-1]) / 2.0
+        upper = torch.cat([centers, bins[..., -1:]], -1)
+        lower = torch.cat([bins[..., :1], centers], -1)
+        bins = lower + (upper - lower) * t_rand
+    return bins.expand(num_rays, num_samples + 1)
+
+
+def spacing_to_euclidean(bins: Tensor, nears: Tensor, fars: Tensor) -> Tensor:
+    """x -> spacing_fn_inv(x * s_far + (1 - x) * s_near) for the piecewise sampler."""
+    s_near, s_far = lindisp_piecewise_fn(nears), lindisp_piecewise_fn(fars)
+    return lindisp_piecewise_inv(bins * s_far + (1 - bins) * s_near)
+
+
+def proposal_density(positions: Tensor, table: Tensor, scalings: Tensor, log2_hashmap_size: int, w0: Tensor, b0: Tensor, w1: Tensor,
+                     b1: Tensor, aabb: Tensor, contraction: bool = True) -> Tensor:
+    """[NS] HashMLPDensityField.get_density (through Field.density_fn): contraction -> (x+2)/4 ->
+    selector mask -> hash grid -> Linear/ReLU/Linear -> trunc_exp * selector.  positions [...,3] -> [...,1]."""
+    pos = positions
+    if contraction:
+        pos = (scene_contraction_inf(pos) + 2.0) / 4.0
+    else:
+        pos = normalized_positions(pos, aabb)
+    selector = ((pos > 0.0) & (pos < 1.0)).all(dim=-1)
+    pos = pos * selector[..., None]
+    flat = pos.reshape(-1, 3)
+    out = []
+    for a in range(0, flat.shape[0], 65536):
+        enc = hash_encode(flat[a : a + 65536], table, scalings, log2_hashmap_size)
+        out.append(mlp_forward(enc, [w0, w1], [b0, b1]))
+    dba = torch.cat(out).view(*pos.shape[:-1], 1)
+    return trunc_exp(dba) * selector[..., None]
+
+
+def pdf_sample(weights: Tensor, existing_bins: Tensor, num_samples: int, u_rand: Optional[Tensor], histogram_padding: float = 0.01,
+               eps: float = 1e-5) -> Tensor:
+    """[NS] PDFSampler.generate_ray_samples (include_original=False) in spacing space.
+
+    weights [R,S] (already annealed), existing_bins [R,S+1] -> new spacing bins [R,num_samples+1]
+    (detached).  ``u_rand``: the torch.rand draw of the reference ([R,1] single jitter or
+    [R,num_samples+1]) or None for the eval-mode midpoints."""
+    num_bins = num_samples + 1
+    weights = weights + histogram_padding
+    weights_sum = torch.sum(weights, dim=-1, keepdim=True)
+    padding = torch.relu(eps - weights_sum)
+    weights = weights + padding / weights.shape[-1]
+    weights_sum = weights_sum + padding
+    pdf = weights / weights_sum
+    cdf = torch.min(torch.ones_like(pdf), torch.cumsum(pdf, dim=-1))
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], dim=-1)
+    u = torch.linspace(0.0, 1.0 - (1.0 / num_bins), steps=num_bins)
+    if u_rand is not None:
+        u = u.expand(*cdf.shape[:-1], num_bins) + u_rand / num_bins
+    else:
+        u = (u + 1.0 / (2 * num_bins)).expand(*cdf.shape[:-1], num_bins)
+    u = u.contiguous()
+    inds = torch.searchsorted(cdf, u, side="right")
+    below = torch.clamp(inds - 1, 0, existing_bins.shape[-1] - 1)
+    above = torch.clamp(inds, 0, existing_bins.shape[-1] - 1)
+    cdf_g0 = torch.gather(cdf, -1, below)
+    bins_g0 = torch.gather(existing_bins, -1, below)
+    cdf_g1 = torch.gather(cdf, -1, above)
+    bins_g1 = torch.gather(existing_bins, -1, above)
+    t = torch.clip(torch.nan_to_num((u - cdf_g0) / (cdf_g1 - cdf_g0), 0), 0, 1)
+    bins = bins_g0 + t * (bins_g1 - bins_g0)
+    return bins.detach()
+
+
+def _outer(t0_starts, t0_ends, t1_starts, t1_ends, y1):
+    cy1 = torch.cat([torch.zeros_like(y1[..., :1]), torch.cumsum(y1, dim=-1)], dim=-1)
+    idx_lo = torch.searchsorted(t1_starts.contiguous(), t0_starts.contiguous(), side="right") - 1
+    idx_lo = torch.clamp(idx_lo, min=0, max=y1.shape[-1] - 1)
+    idx_hi = torch.searchsorted(t1_ends.contiguous(), t0_ends.contiguous(), side="right")
+    idx_hi = torch.clamp(idx_hi, min=0, max=y1.shape[-1] - 1)
+    cy1_lo = torch.take_along_dim(cy1[..., :-1], idx_lo, dim=-1)
+    cy1_hi = torch.take_along_dim(cy1[..., 1:], idx_hi, dim=-1)
+    return cy1_hi - cy1_lo
+
+
+def lossfun_outer(t, w, t_env, w_env):
+    """[NS] losses.lossfun_outer (EPS = 1e-7)."""
+    w_outer = _outer(t[..., :-1], t[..., 1:], t_env[..., :-1], t_env[..., 1:], w_env)
+    return torch.clip(w - w_outer, min=0) ** 2 / (w + 1.0e-7)
+
+
+def interlevel_loss(weights_list: Sequence[Tensor], sdist_list: Sequence[Tensor]) -> Tensor:
+    """[NS] losses.interlevel_loss (fruit_nerf.py:368-370).  weights_list[i] [R,S_i];
+    sdist_list[i] [R,S_i+1] = cat(spacing_starts, spacing_ends[-1]); last entries = final level (detached)."""
+    c = sdist_list[-1].detach()
+    w = weights_list[-1].detach()
+    loss = 0.0
+    for sdist, weights in zip(sdist_list[:-1], weights_list[:-1]):
+        loss = loss + torch.mean(lossfun_outer(c, w, sdist, weights))
+    return loss
+
+
+def distortion_loss(weights: Tensor, sdist: Tensor) -> Tensor:
+    """[NS] losses.distortion_loss on the final level (a metric in FruitNeRF, fruit_nerf.py:400)."""
+    t, w = sdist, weights
+    ut = (t[..., 1:] + t[..., :-1]) / 2
+    dut = torch.abs(ut[..., :, None] - ut[..., None, :])
+    loss_inter = torch.sum(w * torch.sum(w[..., None, :] * dut, dim=-1), dim=-1)
+    loss_intra = torch.sum(w**2 * (t[..., 1:] - t[..., :-1]), dim=-1) / 3
+    return torch.mean(loss_inter + loss_intra)
