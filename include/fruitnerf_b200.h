@@ -16,12 +16,17 @@
  *                        (fruit_nerf/fruit_nerf.py:320-348; fruit_nerf/fruit_field.py:168-301)
  *   fnr_render_backward  autograd of the above (the reference gets it from torch/tcnn autograd;
  *                        loss inputs of fruit_nerf/fruit_nerf.py:359-366)
- *   fnr_field_forward    FruitField.forward alone, per-sample RGB/SEMANTICS/DENSITY
- *                        (fruit_nerf/fruit_field.py:283-301)
+ *                        -- with only the sample_* outputs requested (ray-level pointers NULL)
+ *                        this is FruitField.forward alone (fruit_nerf/fruit_field.py:283-301)
  *   fnr_export_forward   FruitModel.get_export_outputs + the threshold/selection loop body of
  *                        sample_volume (fruit_nerf/fruit_nerf.py:251-269;
  *                        fruit_nerf/export/exporter_utils.py:100-153;
  *                        fruit_nerf/components/ray_samplers.py:54-104)
+ *   fnr_proposal_weights_forward/backward, fnr_pdf_sample, fnr_interlevel_loss
+ *                        the proposal stage FruitModel builds from nerfstudio parts
+ *                        (fruit_nerf/fruit_nerf.py:149-206 construction, :320-321 call, :361-364
+ *                        interlevel loss): HashMLPDensityField.get_density + get_weights,
+ *                        PDFSampler.generate_ray_samples, nerfstudio losses.interlevel_loss
  */
 #ifndef FRUITNERF_B200_H
 #define FRUITNERF_B200_H

@@ -57,7 +57,7 @@ def test_proposal_weights_forward_backward(native_lib, cuda_device, levels, max_
     named = dict(net.named_parameters())
     for key in ("encoding.hash_table", "mlp_base.1.layers.0.weight", "mlp_base.1.layers.0.bias", "mlp_base.1.layers.1.weight",
                 "mlp_base.1.layers.1.bias"):
-        assert_rel(named[key].grad, sd_ref[key].grad, rel=3e-3, floor=0.25, what=f"grad {key}")
+        assert_rel(named[key].grad, sd_ref[key].grad, rel=3e-3, floor=0.5, what=f"grad {key}")
 
 
 @pytest.mark.parametrize("mode", ["eval", "single_jitter", "per_bin"])
