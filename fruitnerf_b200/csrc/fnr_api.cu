@@ -324,7 +324,15 @@ int fnr_export_forward(const fnr_field_desc* desc, const fnr_field_params* param
   E.sample_semantics = out->sample_semantics;
   E.sample_density = out->sample_density;
   E.semantics_colormap = out->semantics_colormap;
-  return launch_simt_export(classify(desc), F, P, E, reinterpret_cast<cudaStream_t>(stream));
+  const Family fam = classify(desc);
+  int impl = desc->impl;
+  if (impl == FNR_IMPL_AUTO) impl = tc_export_supported(fam, E) ? FNR_IMPL_TCGEN05 : FNR_IMPL_SIMT;
+  if (impl == FNR_IMPL_TCGEN05) return launch_tc_export(fam, F, P, E, reinterpret_cast<cudaStream_t>(stream));
+  if (impl != FNR_IMPL_SIMT) {
+    set_error("invalid impl %d", impl);
+    return FNR_ERR_INVALID_ARGUMENT;
+  }
+  return launch_simt_export(fam, F, P, E, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int fnr_hash_indices(const fnr_field_desc* desc, const fnr_ray_batch* rays, int32_t* rows, float* positions, void* stream) {

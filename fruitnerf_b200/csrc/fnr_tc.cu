@@ -85,7 +85,28 @@ struct TcArgs {
   KComposite Cm;
   int rays_per_group;
   int composite;
+  KExport E;  // kExport instantiation only: rays come from (origins, normal, bins) and the per-group stage compacts
 };
+
+// one atomic per warp and output set: returns the claimed base row, rank_out = this lane's offset
+__device__ __forceinline__ int warp_claim_rows(int* counter, bool pred, int lane, int& rank_out) {
+  const unsigned m = __ballot_sync(kFullMask, pred);
+  int basev = 0;
+  if (m) {
+    const int leader = __ffs(m) - 1;
+    if (lane == leader) basev = atomicAdd(counter, __popc(m));
+    basev = __shfl_sync(kFullMask, basev, leader);
+  }
+  rank_out = __popc(m & ((1u << lane) - 1u));
+  return basev;
+}
+
+// UniformSamplerWithNoise in eval mode: t = bins*far + (1-bins)*near (components/ray_samplers.py:89-94)
+__device__ __forceinline__ void export_interval(const KExport& E, int s, float& t0, float& t1) {
+  const float b0 = __ldg(E.bins + s), b1 = __ldg(E.bins + s + 1);
+  t0 = __fadd_rn(__fmul_rn(b0, E.far_plane), __fmul_rn(__fsub_rn(1.0f, b0), E.near_plane));
+  t1 = __fadd_rn(__fmul_rn(b1, E.far_plane), __fmul_rn(__fsub_rn(1.0f, b1), E.near_plane));
+}
 
 // 32-column epilogue of the thread pair (row, half): v = f(column, accumulator) -> chunks 4*half.. of a K=64 tile.
 template <class Fn>
@@ -103,6 +124,7 @@ __device__ __forceinline__ void epi32(uint32_t taddr32, uint8_t* tile, int row, 
   }
 }
 
+template <bool kExport>
 __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -182,7 +204,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
   const bool issue_warp = (warp & 7) == 0;
   const int bar_id = 1 + slot;
 
-  const int S = a.Rr.S, R = a.Rr.R;
+  const int S = kExport ? a.E.S : a.Rr.S, R = kExport ? a.E.B : a.Rr.R;
   const int G = a.rays_per_group;
   const int num_groups = (R + G - 1) / G;
   const float2* __restrict__ table = reinterpret_cast<const float2*>(P.hash_table);
@@ -218,10 +240,17 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
       const int lc = valid ? local : pts - 1;
       const int ray = ray0 + lc / S;
       const size_t gp = (size_t)ray0 * S + lc;  // global point index
-      const float* o = a.Rr.origins + 3 * (size_t)ray;
-      const float* d = a.Rr.directions + 3 * (size_t)ray;
+      const float* o = (kExport ? a.E.origins : a.Rr.origins) + 3 * (size_t)ray;
+      const float* d = kExport ? a.E.normal : a.Rr.directions + 3 * (size_t)ray;
+      float t0, t1;
+      if constexpr (kExport) {
+        export_interval(a.E, lc % S, t0, t1);
+      } else {
+        t0 = __ldg(a.Rr.starts + gp);
+        t1 = __ldg(a.Rr.ends + gp);
+      }
       bool sel;
-      const Vec3 pos = field_position(o, d, __ldg(a.Rr.starts + gp), __ldg(a.Rr.ends + gp), F.position_mode, F.aabb, sel);
+      const Vec3 pos = field_position(o, d, t0, t1, F.position_mode, F.aabb, sel);
 
       // ---- gather + trilinear blend: this thread's 8 levels -> chunks 2*half, 2*half+1 of the encoding tile (aliases Q)
       {
@@ -279,7 +308,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
       // (the encoding tile in Q is dead: its GEMM completed before epilogue 1 ran)
       if (half == 0) {
         float sh[SHD];
-        sh_degree4(__ldg(d), __ldg(d + 1), __ldg(d + 2), sh);
+        sh_degree4(d[0], d[1], d[2], sh);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           float v[8];
@@ -288,7 +317,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
           store_chunk(tQ, 128 * 64 * 2, row, j, v);
         }
       } else {
-        const float* app = (F.appearance_mode == FNR_APP_PER_CAMERA)
+        const float* app = (!kExport && F.appearance_mode == FNR_APP_PER_CAMERA)
                                ? P.app_embedding + (size_t)__ldg(a.Rr.camera_indices + ray) * APP
                                : nullptr;
 #pragma unroll
@@ -366,9 +395,67 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
 #undef FNR_SLOT_ISSUE
 #undef FNR_SLOT_WAIT
 
-    // ---- per-group: write per-sample outputs, composite one ray per warp -------------------------
+    // ---- per-group: write per-sample outputs, then composite one ray per warp (render) or threshold + compact (export)
     __syncthreads();
-    {
+    if constexpr (kExport) {
+      // FruitModel.get_export_outputs + the selection body of sample_volume (fruit_nerf.py:251-269;
+      // export/exporter_utils.py:111-153): three output sets, warp-aggregated row claims
+      const KExport& E = a.E;
+      const size_t gbase = (size_t)ray0 * S;
+      const int padded = (pts + 31) & ~31;
+      for (int i = tid; i < padded; i += kCtaThreads) {
+        const bool in = i < pts;
+        const int ic = in ? i : pts - 1;
+        const float* q = s_samples + 5 * ic;
+        const size_t p = gbase + ic;
+        float t0, t1;
+        export_interval(E, ic % S, t0, t1);
+        bool sel;
+        Vec3 world;
+        (void)field_position(E.origins + 3 * (size_t)(ray0 + ic / S), E.normal, t0, t1, FNR_POS_AABB, F.aabb, sel, &world);
+        const float density = q[0], logit = q[4];
+        const float sg = sigmoidf_(logit);
+        const int label = (sg - E.label_thr > 0.f) ? 1 : 0;  // heaviside(sigmoid(logit) - thr, 0)
+        if (in) {
+          if (E.sample_density) E.sample_density[p] = density;
+          if (E.sample_semantics) E.sample_semantics[p] = logit;
+          if (E.semantics_colormap) E.semantics_colormap[p] = label;
+          if (E.sample_rgb) {
+            E.sample_rgb[3 * p] = q[1];
+            E.sample_rgb[3 * p + 1] = q[2];
+            E.sample_rgb[3 * p + 2] = q[3];
+          }
+          if (E.point_location) {
+            E.point_location[3 * p] = world.x;
+            E.point_location[3 * p + 1] = world.y;
+            E.point_location[3 * p + 2] = world.z;
+          }
+        }
+        const bool m_den = in && (density >= E.density_min);
+        const bool m_sem = in && (logit >= E.logit_min);
+        const bool m_lab = in && ((float)label >= 0.999f);
+        const bool keep[3] = {m_lab && m_den, m_sem && m_den, m_den};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          int rank;
+          const int basev = warp_claim_rows(E.counts + k, keep[k], lane, rank);
+          if (keep[k] && E.rows[k]) {
+            const int orow = basev + rank;
+            if (orow < E.capacity) {
+              float* w = E.rows[k] + 7 * (size_t)orow;
+              w[0] = world.x;
+              w[1] = world.y;
+              w[2] = world.z;
+              w[3] = q[1];
+              w[4] = q[2];
+              w[5] = q[3];
+              w[6] = (k == 2) ? sigmoidf_(density) : sg;
+              if (E.keys[k]) E.keys[k][orow] = E.point_base + (uint64_t)p;
+            }
+          }
+        }
+      }
+    } else {
       const size_t gbase = (size_t)ray0 * S;
       for (int i = tid; i < pts; i += kCtaThreads) {
         const float* q = s_samples + 5 * i;
@@ -381,7 +468,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
         }
       }
     }
-    if (a.composite) {
+    if (!kExport && a.composite) {
       const KComposite& Cm = a.Cm;
       for (int rl = warp; rl < rays_here; rl += kCtaThreads / 32) {
         const int r = ray0 + rl;
@@ -480,6 +567,19 @@ bool tc_supported(Family fam, const KField& F, const KRays& Rr) {
   return fam == kFamilySmall && Rr.S >= 1 && Rr.S <= kMaxGroupPoints;
 }
 
+bool tc_export_supported(Family fam, const KExport& E) { return fam == kFamilySmall && E.S >= 1 && E.S <= kMaxGroupPoints; }
+
+template <bool kExport>
+static int configure_tc_forward() {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_render_forward_kernel<kExport>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tc_render_forward_kernel)");
+    configured = true;
+  }
+  return FNR_OK;
+}
+
 int launch_tc_render_forward(Family fam, const KField& F, const KParams& P, const KRays& Rr, const KFieldOut& O,
                              const KComposite& Cm, cudaStream_t st) {
   if (!tc_supported(fam, F, Rr)) {
@@ -487,13 +587,9 @@ int launch_tc_render_forward(Family fam, const KField& F, const KParams& P, cons
     return FNR_ERR_UNSUPPORTED;
   }
   if (Rr.R == 0) return FNR_OK;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_render_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tc_render_forward_kernel)");
-    configured = true;
-  }
+  if (int rc = configure_tc_forward<false>()) return rc;
   TcArgs a;
+  memset(&a.E, 0, sizeof(a.E));
   a.F = F;
   a.P = P;
   a.Rr = Rr;
@@ -503,8 +599,31 @@ int launch_tc_render_forward(Family fam, const KField& F, const KParams& P, cons
   a.composite = Cm.rgb || Cm.accumulation || Cm.depth || Cm.depth_index || Cm.semantics || Cm.weights;
   const int groups = (Rr.R + a.rays_per_group - 1) / a.rays_per_group;
   const int grid = groups < sm_count() ? groups : sm_count();
-  tc_render_forward_kernel<<<grid, kCtaThreads, kSmemBytes, st>>>(a);
+  tc_render_forward_kernel<false><<<grid, kCtaThreads, kSmemBytes, st>>>(a);
   return check_cuda(cudaGetLastError(), "tc_render_forward_kernel");
+}
+
+// The export path reuses the fused forward (AABB positions, mean appearance embedding) and replaces the
+// compositing stage by the three threshold selections + stream compaction.
+int launch_tc_export(Family fam, const KField& F, const KParams& P, const KExport& E, cudaStream_t st) {
+  if (!tc_export_supported(fam, E)) {
+    set_error("tcgen05 export kernel does not support this shape");
+    return FNR_ERR_UNSUPPORTED;
+  }
+  if (E.B == 0) return FNR_OK;
+  if (int rc = configure_tc_forward<true>()) return rc;
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.F = F;
+  a.F.position_mode = FNR_POS_AABB;
+  a.F.appearance_mode = FNR_APP_MEAN;
+  a.P = P;
+  a.E = E;
+  a.rays_per_group = pick_rays_per_group(E.S);
+  const int groups = (E.B + a.rays_per_group - 1) / a.rays_per_group;
+  const int grid = groups < sm_count() ? groups : sm_count();
+  tc_render_forward_kernel<true><<<grid, kCtaThreads, kSmemBytes, st>>>(a);
+  return check_cuda(cudaGetLastError(), "tc_render_forward_kernel<export>");
 }
 
 }  // namespace fnr

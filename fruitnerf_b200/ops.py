@@ -265,7 +265,7 @@ class ExportBuffers:
 
 def export_batch(shape: FieldShape, params: Sequence[Tensor], origins: Tensor, normal: Sequence[float], bins: Tensor,
                  near: float, far: float, buffers: ExportBuffers, point_base: int = 0, dense_out: bool = False,
-                 thresholds=(3.0, 70.0, 0.9)) -> Optional[Dict[str, Tensor]]:
+                 thresholds=(3.0, 70.0, 0.9), impl: int = L.FNR_IMPL_AUTO) -> Optional[Dict[str, Tensor]]:
     """One batch of FruitModel.get_export_outputs + the selection of sample_volume
     (fruit_nerf/fruit_nerf.py:251-269; fruit_nerf/export/exporter_utils.py:100-153)."""
     dev = _require_cuda(origins, bins, *params)
@@ -274,7 +274,7 @@ def export_batch(shape: FieldShape, params: Sequence[Tensor], origins: Tensor, n
     bins = _f32c(bins)
     B, S = origins.shape[0], bins.numel() - 1
     params = [p.detach() for p in params]
-    desc = shape.desc(L.FNR_POS_AABB, L.FNR_APP_MEAN)
+    desc = shape.desc(L.FNR_POS_AABB, L.FNR_APP_MEAN, impl)
     pstruct = _params_struct(shape, params)
     xp = L.ExportParams(float(thresholds[0]), float(thresholds[1]), float(thresholds[2]), buffers.capacity)
     out = L.ExportOut()
