@@ -148,6 +148,13 @@ class DensityParams(C.Structure):
     _fields_ = [("hash_table", C.c_void_p), ("w0", C.c_void_p), ("b0", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p)]
 
 
+class AdamTensor(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("n", C.c_int64)]
+
+
+FNR_OPT_ADAM, FNR_OPT_RADAM = 0, 1
+FNR_MAX_ADAM_TENSORS = 48
+
 LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libfruitnerf_b200.so"
 
 # every symbol include/fruitnerf_b200.h declares
@@ -163,6 +170,7 @@ EXPORTED_SYMBOLS = (
     "fnr_proposal_weights_backward",
     "fnr_pdf_sample",
     "fnr_interlevel_loss",
+    "fnr_adam_step",
 )
 
 _lib = None
@@ -207,11 +215,13 @@ def load() -> C.CDLL:
     lib.fnr_proposal_weights_backward.argtypes = [C.POINTER(DensityDesc), C.POINTER(DensityParams), C.POINTER(RayBatch), C.c_void_p, C.c_void_p,
                                                   C.c_void_p, C.POINTER(DensityParams), C.c_void_p]
     lib.fnr_pdf_sample.restype = C.c_int
-    lib.fnr_pdf_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float,
+    lib.fnr_pdf_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_float,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.fnr_interlevel_loss.restype = C.c_int
     lib.fnr_interlevel_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
                                         C.c_void_p, C.c_void_p]
+    lib.fnr_adam_step.restype = C.c_int
+    lib.fnr_adam_step.argtypes = [C.POINTER(AdamTensor), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     if lib.fnr_version() != 1:
         raise FruitNerfNativeError(f"ABI version mismatch: library reports {lib.fnr_version()}")
     _lib = lib

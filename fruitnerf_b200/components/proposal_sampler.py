@@ -29,11 +29,29 @@ class ProposalNetworkSampler(nn.Module):
         self.single_jitter = single_jitter
         self.histogram_padding = 0.01  # PDFSampler default
         self._anneal = 1.0
+        self._anneal_dev: Optional[torch.Tensor] = None  # device copy of the exponent (enable_device_anneal)
+        self._anneal_staged = None
+        self.force_updated: Optional[bool] = None  # set by a CUDA-graph trainer that picks the schedule branch itself
         self._steps_since_update = 0
         self._step = 0
 
     def set_anneal(self, anneal: float) -> None:
         self._anneal = anneal
+        if self._anneal_staged is not None:
+            self._anneal_staged.upload([float(anneal)])
+
+    def enable_device_anneal(self, device) -> None:
+        """Keep the annealing exponent in device memory: the kernels read it there, so the schedule can move between
+        replays of a captured graph."""
+        from ..optim import StagedDeviceBuffer
+
+        self._anneal_staged = StagedDeviceBuffer(1, torch.device(device))
+        self._anneal_dev = self._anneal_staged.device_buffer
+        self._anneal_staged.upload([float(self._anneal)])
+
+    def wants_update(self) -> bool:
+        """nerfstudio ProposalNetworkSampler: run the proposal networks with gradients on this iteration?"""
+        return bool(self._steps_since_update > self.update_sched(self._step) or self._step < 10)
 
     def step_cb(self, step):
         self._step = step
@@ -49,7 +67,8 @@ class ProposalNetworkSampler(nn.Module):
         if self.training:  # PDFSampler(train_stratified=True)
             u_rand = torch.rand((R, 1) if self.single_jitter else (R, num_samples + 1), device=dev)
         existing = torch.cat([prev.spacing_starts[..., 0], prev.spacing_ends[..., -1:, 0]], dim=-1)
-        bins, starts, ends = ops.pdf_sample(weights, existing, num_samples, u_rand, self._anneal, ray_bundle.nears, ray_bundle.fars,
+        anneal = self._anneal_dev if self._anneal_dev is not None else self._anneal
+        bins, starts, ends = ops.pdf_sample(weights, existing, num_samples, u_rand, anneal, ray_bundle.nears, ray_bundle.fars,
                                             self.histogram_padding)
         return ray_bundle.get_ray_samples(bin_starts=starts[..., None], bin_ends=ends[..., None], spacing_starts=bins[..., :-1, None],
                                           spacing_ends=bins[..., 1:, None], spacing_to_euclidean_fn=prev.spacing_to_euclidean_fn)
@@ -60,7 +79,7 @@ class ProposalNetworkSampler(nn.Module):
         weights_list, ray_samples_list = [], []
         n = self.num_proposal_network_iterations
         weights, ray_samples = None, None
-        updated = self._steps_since_update > self.update_sched(self._step) or self._step < 10
+        updated = self.wants_update() if self.force_updated is None else self.force_updated
         for i_level in range(n + 1):
             is_prop = i_level < n
             num_samples = self.num_proposal_samples_per_ray[i_level] if is_prop else self.num_nerf_samples_per_ray

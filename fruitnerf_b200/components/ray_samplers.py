@@ -30,8 +30,13 @@ class SpacedSampler(nn.Module):
         return self.generate_ray_samples(ray_bundle, num_samples)
 
     def spacing_bins(self, num_rays: int, num_samples: int, device) -> Tensor:
-        # the reference builds the bins on the host and moves them (ray_samplers.py:75)
-        bins = torch.linspace(0.0, 1.0, num_samples + 1).to(device)[None, ...]
+        # the reference builds the bins on the host and moves them (ray_samplers.py:75); cached per (size, device) so that
+        # no host->device copy happens per call (and none inside a CUDA-graph capture)
+        cache = self.__dict__.setdefault("_bins_cache", {})
+        key = (num_samples, str(device))
+        if key not in cache:
+            cache[key] = torch.linspace(0.0, 1.0, num_samples + 1).to(device)[None, ...]
+        bins = cache[key]
         if self.train_stratified and self.training:
             if self.single_jitter:
                 t_rand = torch.rand((num_rays, 1), dtype=bins.dtype, device=bins.device)

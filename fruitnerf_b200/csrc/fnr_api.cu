@@ -427,8 +427,9 @@ int fnr_proposal_weights_backward(const fnr_density_desc* desc, const fnr_densit
 }
 
 int fnr_pdf_sample(const float* weights, const float* existing_bins, int32_t num_rays, int32_t num_existing, int32_t num_samples,
-                   const float* u_base, const float* u_rand, int32_t u_stride, float anneal, float histogram_padding, const float* nears,
-                   const float* fars, float* new_bins, float* starts, float* ends, void* stream) {
+                   const float* u_base, const float* u_rand, int32_t u_stride, float anneal, const float* anneal_dev,
+                   float histogram_padding, const float* nears, const float* fars, float* new_bins, float* starts, float* ends,
+                   void* stream) {
   int max_levels, hidden, max_bins;
   proposal_limits(&max_levels, &hidden, &max_bins);
   if (num_rays < 0 || num_existing < 1 || num_samples < 1 || num_existing > max_bins || num_samples > max_bins) {
@@ -444,7 +445,7 @@ int fnr_pdf_sample(const float* weights, const float* existing_bins, int32_t num
     return FNR_ERR_INVALID_ARGUMENT;
   }
   KPdf A{num_rays, num_existing, num_samples, weights, existing_bins, u_base, u_rand, u_stride, anneal, histogram_padding, 1e-5f,
-         nears,    fars,         new_bins,    starts,  ends};
+         anneal_dev, nears, fars, new_bins, starts, ends};
   return launch_pdf_sample(A, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -462,6 +463,31 @@ int fnr_interlevel_loss(const float* c, const float* w, const float* cp, const f
   }
   KInterlevel A{num_rays, sc, sp, c, w, cp, wp, num_rays > 0 ? mult / ((float)num_rays * (float)sc) : 0.f, loss, d_wp};
   return launch_interlevel_loss(A, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fnr_adam_step(const fnr_adam_tensor* tensors, int32_t count, int32_t kind, const float* hyper, void* stream) {
+  if (count < 0 || count > kMaxAdamTensors || (count > 0 && !tensors) || !hyper || (kind != FNR_OPT_ADAM && kind != FNR_OPT_RADAM)) {
+    set_error("invalid arguments to fnr_adam_step (count %d, max %d)", count, kMaxAdamTensors);
+    return FNR_ERR_INVALID_ARGUMENT;
+  }
+  KAdam A;
+  A.count = count;
+  for (int i = 0; i < count; ++i) {
+    const fnr_adam_tensor& t = tensors[i];
+    if (t.n < 0 || (t.n > 0 && (!t.param || !t.grad || !t.exp_avg || !t.exp_avg_sq))) {
+      set_error("fnr_adam_step: tensor %d has NULL pointers", i);
+      return FNR_ERR_INVALID_ARGUMENT;
+    }
+    A.t[i].param = t.param;
+    A.t[i].grad = t.grad;
+    A.t[i].exp_avg = t.exp_avg;
+    A.t[i].exp_avg_sq = t.exp_avg_sq;
+    A.t[i].n = t.n;
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(t.param) | reinterpret_cast<uintptr_t>(t.grad) |
+                           reinterpret_cast<uintptr_t>(t.exp_avg) | reinterpret_cast<uintptr_t>(t.exp_avg_sq);
+    A.t[i].vec4 = (bits & 15u) == 0;
+  }
+  return launch_adam(A, kind == FNR_OPT_RADAM, hyper, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -97,6 +97,22 @@ struct KExport {
   int64_t* semantics_colormap;
 };
 
+// ---- optimiser (fnr_optim.cu) ----
+constexpr int kMaxAdamTensors = 48;
+struct KAdamTensor {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  long long n;
+  int vec4;  // all four pointers 16-byte aligned
+};
+struct KAdam {
+  int count;
+  KAdamTensor t[kMaxAdamTensors];
+};
+int launch_adam(const KAdam& A, int radam, const float* hyper, cudaStream_t st);
+
 // ---- proposal stage (fnr_proposal.cu) ----
 struct KDensity {  // nerfstudio HashMLPDensityField: hash grid (L levels, F=2) -> Linear(2L,16) -> ReLU -> Linear(16,1)
   int L, log2T, position_mode;
@@ -117,6 +133,7 @@ struct KPdf {
   const float* u_rand;         // NULL (bin centres) | [R*u_stride]
   int u_stride;                // 1 = single jitter per ray, num_samples+1 = per bin
   float anneal, hist_padding, eps;
+  const float* anneal_dev;     // optional device scalar overriding `anneal` (CUDA-graph replays with a moving schedule)
   const float* nears;          // [R]
   const float* fars;           // [R]
   float* new_bins;             // [R,num_samples+1]

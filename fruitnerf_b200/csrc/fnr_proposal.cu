@@ -279,11 +279,12 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) pdf_sample_kernel(KPdf A)
   for (int r = blockIdx.x * kWarpsPerBlock + wib; r < A.R; r += gridDim.x * kWarpsPerBlock) {
     const float* w = A.weights + (size_t)r * S;
     const float* eb = A.existing_bins + (size_t)r * (S + 1);
+    const float anneal = A.anneal_dev ? __ldg(A.anneal_dev) : A.anneal;
     // weights^anneal + histogram padding, then the zero-weight guard of the reference
     float part = 0.f;
     for (int i = lane; i < S; i += 32) {
       float v = w[i];
-      if (A.anneal != 1.0f) v = powf(v, A.anneal);
+      if (anneal != 1.0f) v = powf(v, anneal);
       part += v + A.hist_padding;
     }
     float wsum = warp_sum(part);
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) pdf_sample_kernel(KPdf A)
       float pdf = 0.f;
       if (i < S) {
         float v = w[i];
-        if (A.anneal != 1.0f) v = powf(v, A.anneal);
+        if (anneal != 1.0f) v = powf(v, anneal);
         pdf = (v + A.hist_padding + pad_each) / wsum;
       }
       const float incl = warp_incl_scan(pdf, lane);

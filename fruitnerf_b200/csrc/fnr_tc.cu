@@ -22,6 +22,8 @@
 //
 // Shapes: the fruit_nerf family (geo 15, semantic 15-64-64, colour 63-64-64-3).  Everything else is
 // served by the simt kernels (tc_supported() == false).
+#include <cstdio>
+#include <cstdlib>
 #include "fnr_common.cuh"
 #include "fnr_kernels.h"
 #include "fnr_tcgen05.cuh"
@@ -85,6 +87,7 @@ struct TcArgs {
   KComposite Cm;
   int rays_per_group;
   int composite;
+  int debug;  // FNR_DEBUG_FWD: block 0 prints per-phase cycle totals (timing experiments only)
   KExport E;  // kExport instantiation only: rays come from (origins, normal, bins) and the per-group stage compacts
 };
 
@@ -227,6 +230,16 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
   phase ^= 1;            \
   fence_after_sync();
 
+  long long t_gather = 0, t_chain = 0, t_group = 0, t_mark = 0;
+  const bool prof = a.debug && blockIdx.x == 0 && (tid & 255) == 0;
+#define FNR_TICK(acc)                  \
+  if (prof) {                          \
+    const long long now_ = clock64();  \
+    acc += now_ - t_mark;              \
+    t_mark = now_;                     \
+  }
+  if (prof) t_mark = clock64();
+
   for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
     const int ray0 = group * G;
     const int rays_here = min(G, R - ray0);
@@ -298,6 +311,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
           store_chunk(tQ, 128 * K_BASE0 * 2, row, 2 * half + jj, v);
         }
       }
+      FNR_TICK(t_gather)
       FNR_SLOT_ISSUE(issue_gemm<K_BASE0, N_BASE0>(tmem_slot + C_R0, aQ, wBase + OFF_W_BASE0))
 
       // ---- epilogue 1: h1 = relu(base0 + b) -> P ; then the geo-independent colour-input chunks -> Q ------
@@ -391,6 +405,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
         }
       }
       fence_before_sync();  // order this round's TMEM reads before the next round's MMAs
+      FNR_TICK(t_chain)
     }
 #undef FNR_SLOT_ISSUE
 #undef FNR_SLOT_WAIT
@@ -537,7 +552,10 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
       }
     }
     __syncthreads();  // s_samples is rewritten by the next group
+    FNR_TICK(t_group)
   }
+  if (prof) printf("fwd slot %d: gather %lld chain %lld group-stage %lld cycles\n", slot, t_gather, t_chain, t_group);
+#undef FNR_TICK
 
   fence_before_sync();
   __syncthreads();
@@ -596,6 +614,7 @@ int launch_tc_render_forward(Family fam, const KField& F, const KParams& P, cons
   a.O = O;
   a.Cm = Cm;
   a.rays_per_group = pick_rays_per_group(Rr.S);
+  a.debug = getenv("FNR_DEBUG_FWD") != nullptr;
   a.composite = Cm.rgb || Cm.accumulation || Cm.depth || Cm.depth_index || Cm.semantics || Cm.weights;
   const int groups = (Rr.R + a.rays_per_group - 1) / a.rays_per_group;
   const int grid = groups < sm_count() ? groups : sm_count();

@@ -1,9 +1,11 @@
-"""Export-side datamanager pieces of the plugin surface (fruit_nerf/data/fruit_datamanager.py).
+"""Datamanager of the plugin surface (fruit_nerf/data/fruit_datamanager.py).
 
-In scope: ``get_corners_of_aabb`` (42-68), ``sample_surface_points`` (71-121),
-``FruitDataManager.setup_inference`` (157-172) and ``next_sample_volume`` (199-204) -- they define
-the export ray grid.  Image loading / pixel sampling (the rest of the reference datamanager) is
-host-side I/O outside the hot path and is not rebuilt here.
+Export side: ``get_corners_of_aabb`` (42-68), ``sample_surface_points`` (71-121),
+``FruitDataManager.setup_inference`` (157-172) and ``next_sample_volume`` (199-204) -- they define the export
+ray grid.  Training side (section 8f rank 3): ``next_train`` / ``next_eval`` (183-215) over an in-memory data set
+(images + fruit masks + cameras resident on the GPU, e.g. ``data.synthetic_scene``): uniform pixel sampling across
+all training images and pinhole ray generation on the device -- no host work or H2D copy per step.  Reading
+images from disk (nerfstudio's dataparser / dataloader machinery) is host I/O outside the path.
 """
 from __future__ import annotations
 
@@ -61,6 +63,8 @@ class FruitDataManagerConfig(InstantiateConfig):
     _target: Type = field(default_factory=lambda: FruitDataManager)
     train_num_rays_per_batch: int = 4096
     eval_num_rays_per_batch: int = 4096
+    synthetic_scene: Optional[Dict] = None  # kwargs of data.synthetic_scene.make_apple_scene (no data set on disk)
+    seed: int = 0
 
 
 class FruitDataManager(nn.Module):
@@ -78,7 +82,59 @@ class FruitDataManager(nn.Module):
         self.train_count = 0
         self.eval_count = 0
         self.train_dataset = kwargs.get("train_dataset")
+        self.eval_dataset = kwargs.get("eval_dataset")
+        if self.train_dataset is None and config.synthetic_scene is not None:
+            from .synthetic_scene import make_apple_scene
+
+            self.train_dataset, self.eval_dataset = make_apple_scene(**config.synthetic_scene)
+        if self.train_dataset is not None and hasattr(self.train_dataset, "to"):
+            self.train_dataset = self.train_dataset.to(device)
+            if self.eval_dataset is not None:
+                self.eval_dataset = self.eval_dataset.to(device)
         self.orthographic_ray_generator: Optional[OrthographicRayGenerator] = None
+        self._gen: Optional[torch.Generator] = None
+
+    # ---- training / evaluation batches (fruit_datamanager.py:183-215) ------------------------------------
+    def _generator(self) -> torch.Generator:
+        if self._gen is None:
+            self._gen = torch.Generator(device=self.device)
+            self._gen.manual_seed(self.config.seed * 7919 + self.local_rank)  # each rank draws its own batch (fruit_pipeline.py:97-99)
+        return self._gen
+
+    def _pixel_batch(self, ds, num_rays: int) -> Tuple[RayBundle, Dict]:
+        """nerfstudio PixelSampler.sample_method (uniform over images x rows x cols) + RayGenerator."""
+        from .synthetic_scene import camera_rays
+
+        cams = ds.cameras
+        N, H, W = len(ds), cams.height, cams.width
+        dev = ds.images.device
+        # CUDA: the default generator (seeded per rank by the trainer) -- the one torch can advance inside a captured graph
+        r = torch.rand((num_rays, 3), device=dev, generator=None if dev.type == "cuda" else self._generator())
+        extent = self.__dict__.setdefault("_extent_cache", {})
+        key = (N, H, W, str(dev))
+        if key not in extent:
+            extent[key] = torch.tensor([N, H, W], dtype=torch.float32).to(dev)
+        idx = torch.floor(r * extent[key]).long()
+        ci, ys, xs = idx[:, 0], idx[:, 1], idx[:, 2]
+        o, d = camera_rays(cams.camera_to_worlds[ci], cams.fx, cams.fy, cams.cx, cams.cy, ys, xs)
+        bundle = RayBundle(origins=o.contiguous(), directions=d.contiguous(),
+                           pixel_area=torch.full((num_rays, 1), 1.0 / (cams.fx * cams.fy), device=o.device), camera_indices=ci[:, None])
+        batch = {"image": ds.images[ci, ys, xs], "fruit_mask": ds.fruit_masks[ci, ys, xs], "indices": idx}
+        return bundle, batch
+
+    def next_train(self, step: int) -> Tuple[RayBundle, Dict]:
+        self.train_count += 1
+        return self._pixel_batch(self.train_dataset, self.config.train_num_rays_per_batch)
+
+    def next_eval(self, step: int) -> Tuple[RayBundle, Dict]:
+        self.eval_count += 1
+        return self._pixel_batch(self.eval_dataset, self.config.eval_num_rays_per_batch)
+
+    def next_eval_image(self, step: int) -> Tuple[int, RayBundle, Dict]:
+        ds = self.eval_dataset
+        i = self.eval_count % len(ds)
+        self.eval_count += 1
+        return i, ds.cameras.generate_rays(i), {"image": ds.images[i], "fruit_mask": ds.fruit_masks[i]}
 
     def setup_inference(self, aabb, num_points) -> int:
         """fruit_datamanager.py:157-172: ray grid for the uniform volume; returns the ray count."""

@@ -227,8 +227,10 @@ class FruitModel(nn.Module):
         outputs["semantics"] = out["semantics"].view(R, 1)
         semantic_labels = torch.sigmoid(outputs["semantics"].detach())
         threshold = 0.9
-        semantic_labels = torch.heaviside(semantic_labels - threshold, torch.tensor(0.0, device=semantic_labels.device)).to(torch.long)
-        cmap = self.colormap.to(semantic_labels.device)[semantic_labels]
+        semantic_labels = torch.heaviside(semantic_labels - threshold, torch.zeros((), device=semantic_labels.device)).to(torch.long)
+        if self.colormap.device != semantic_labels.device:  # moved once, not per call (and never inside a graph capture)
+            self.colormap = self.colormap.to(semantic_labels.device)
+        cmap = self.colormap[semantic_labels]
         outputs["semantics_colormap"] = cmap.repeat(1, 3) if self.test_mode == "inference" else cmap  # fruit_nerf.py:312 / 355
         return outputs
 

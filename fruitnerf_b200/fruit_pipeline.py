@@ -85,6 +85,31 @@ class FruitPipeline(nn.Module):
         loss_dict = self.model.get_loss_dict(model_outputs, batch, metrics_dict)
         return model_outputs, loss_dict, metrics_dict
 
+    @torch.no_grad()
+    def get_eval_image_metrics_and_images(self, step: int):
+        """fruit_pipeline.py:165-190: render one held-out image, PSNR against the ground truth (the reference's SSIM /
+        LPIPS come from torchmetrics, which is not available offline), plus the fruit-mask agreement of the semantic map."""
+        was_training = self.training
+        self.eval()
+        image_idx, camera_ray_bundle, batch = self.datamanager.next_eval_image(step)
+        outputs = self.model.get_outputs_for_camera_ray_bundle(camera_ray_bundle)
+        image = batch["image"].cpu()
+        mse = torch.mean((outputs["rgb"] - image) ** 2)
+        pred_fruit = (torch.sigmoid(outputs["semantics"]) > 0.9).float()
+        gt = batch["fruit_mask"].cpu()
+        inter, union = float((pred_fruit * gt).sum()), float(((pred_fruit + gt) > 0).float().sum())
+        metrics = {"psnr": float(-10.0 * torch.log10(mse)), "fruit_iou": inter / union if union > 0 else 1.0, "image_idx": image_idx,
+                   "num_rays": int(image.shape[0] * image.shape[1])}
+        self.train(was_training)
+        return metrics, {"img": torch.cat([image, outputs["rgb"]], dim=1), "semantics": outputs["semantics"], "depth": outputs["depth"]}
+
+    @torch.no_grad()
+    def get_average_eval_image_metrics(self, step: Optional[int] = None) -> Dict[str, float]:
+        """fruit_pipeline.py:192-227: mean of the per-image metrics over the eval split."""
+        n = len(self.datamanager.eval_dataset)
+        rows = [self.get_eval_image_metrics_and_images(step or 0)[0] for _ in range(n)]
+        return {k: float(sum(r[k] for r in rows) / n) for k in ("psnr", "fruit_iou")}
+
     def sync_gradients(self):
         """Call after ``loss.backward()``: one collective over the flat gradient buffer."""
         flat = ops._Render.last_flat_grad

@@ -376,6 +376,16 @@ def proposal_weights(shape: DensityShape, params: Sequence[Tensor], origins, dir
     return _ProposalWeights.apply(shape, position_mode, origins, directions, starts, ends, *params)
 
 
+_LINSPACE_CACHE: Dict = {}
+
+
+def _linspace_cached(lo: float, hi: float, steps: int, dev) -> Tensor:
+    key = (lo, hi, steps, str(dev))
+    if key not in _LINSPACE_CACHE:
+        _LINSPACE_CACHE[key] = torch.linspace(lo, hi, steps=steps, device=dev)
+    return _LINSPACE_CACHE[key]
+
+
 def pdf_sample(weights: Tensor, existing_bins: Tensor, num_samples: int, u_rand: Optional[Tensor], anneal: float, nears: Tensor, fars: Tensor,
                histogram_padding: float = 0.01):
     """PDFSampler + spacing->euclidean map.  Returns (new spacing bins [R,n+1], starts [R,n], ends [R,n]); no gradient
@@ -387,7 +397,7 @@ def pdf_sample(weights: Tensor, existing_bins: Tensor, num_samples: int, u_rand:
     nears, fars = _f32c(nears.reshape(-1)), _f32c(fars.reshape(-1))
     nb = num_samples + 1
     # as the reference: torch.linspace on the device the cdf lives on
-    u_base = torch.linspace(0.0, 1.0 - (1.0 / nb), steps=nb, device=dev)
+    u_base = _linspace_cached(0.0, 1.0 - (1.0 / nb), nb, dev)
     stride = 0
     if u_rand is not None:
         u_rand = _f32c(u_rand)
@@ -395,8 +405,11 @@ def pdf_sample(weights: Tensor, existing_bins: Tensor, num_samples: int, u_rand:
     bins = torch.empty((R, nb), dtype=torch.float32, device=dev)
     starts = torch.empty((R, num_samples), dtype=torch.float32, device=dev)
     ends = torch.empty((R, num_samples), dtype=torch.float32, device=dev)
+    anneal_dev = None
+    if torch.is_tensor(anneal):  # device scalar: the schedule advances between CUDA-graph replays
+        anneal_dev, anneal = _f32c(anneal), 1.0
     L.check(lib.fnr_pdf_sample(weights.data_ptr(), existing_bins.data_ptr(), R, S, num_samples, u_base.data_ptr(), _ptr(u_rand), stride,
-                               float(anneal), float(histogram_padding), nears.data_ptr(), fars.data_ptr(), bins.data_ptr(),
+                               float(anneal), _ptr(anneal_dev), float(histogram_padding), nears.data_ptr(), fars.data_ptr(), bins.data_ptr(),
                                starts.data_ptr(), ends.data_ptr(), _stream(dev)))
     return bins, starts, ends
 

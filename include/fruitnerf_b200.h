@@ -27,6 +27,8 @@
  *                        (fruit_nerf/fruit_nerf.py:149-206 construction, :320-321 call, :361-364
  *                        interlevel loss): HashMLPDensityField.get_density + get_weights,
  *                        PDFSampler.generate_ray_samples, nerfstudio losses.interlevel_loss
+ *   fnr_adam_step        torch.optim.Adam / RAdam over a param group (nerfstudio Optimizers; optimiser
+ *                        settings fruit_nerf/fruit_nerf_config.py:47-56, 90-103, 140-153)
  */
 #ifndef FRUITNERF_B200_H
 #define FRUITNERF_B200_H
@@ -213,16 +215,36 @@ int fnr_proposal_weights_backward(const fnr_density_desc* desc, const fnr_densit
  *   weights [R,S], existing_bins [R,S+1] (spacing space), u_base [num_samples+1] = linspace(0, 1-1/NB, NB)
  *   (made by the caller, as the reference does with torch.linspace), u_rand NULL (bin centres, eval) or
  *   [R*u_stride] uniform draws (u_stride 1 = single jitter, num_samples+1 = per bin), weights are raised to
- *   `anneal` first.  Outputs: new_bins [R,num_samples+1] (spacing), starts/ends [R,num_samples] (euclidean). */
+ *   `anneal` first (`anneal_dev`, when non-NULL, is a device scalar that overrides it: the annealing schedule
+ *   can then advance between replays of a captured CUDA graph).  Outputs: new_bins [R,num_samples+1] (spacing), starts/ends [R,num_samples] (euclidean). */
 int fnr_pdf_sample(const float* weights, const float* existing_bins, int32_t num_rays, int32_t num_existing,
                    int32_t num_samples, const float* u_base, const float* u_rand, int32_t u_stride, float anneal,
-                   float histogram_padding, const float* nears, const float* fars, float* new_bins, float* starts,
-                   float* ends, void* stream);
+                   const float* anneal_dev, float histogram_padding, const float* nears, const float* fars,
+                   float* new_bins, float* starts, float* ends, void* stream);
 
 /* losses.interlevel_loss for ONE proposal level: adds mult * mean(lossfun_outer(c, w, cp, wp)) to *loss and
  * writes d loss / d wp into d_wp [R,Sp] (may be NULL).  c [R,Sc+1], w [R,Sc] are the (detached) final level. */
 int fnr_interlevel_loss(const float* c, const float* w, const float* cp, const float* wp, int32_t num_rays, int32_t sc,
                         int32_t sp, float mult, float* loss, float* d_wp, void* stream);
+
+/* One tensor of an optimiser param group: parameter, its gradient and the two Adam moments (all fp32, n elements). */
+typedef struct fnr_adam_tensor {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t n;
+} fnr_adam_tensor;
+
+#define FNR_OPT_ADAM 0
+#define FNR_OPT_RADAM 1
+#define FNR_MAX_ADAM_TENSORS 48
+
+/* torch.optim.Adam / RAdam step (amsgrad off, weight decay 0 -- the optimisers of
+ * fruit_nerf/fruit_nerf_config.py:47-56, 90-103) for `count` tensors in ONE launch.  `tensors` is a HOST array;
+ * `hyper` is a DEVICE array of 8 floats {lr, beta1, beta2, eps, 1-beta1^t, 1-beta2^t, radam_rect (<0: not
+ * rectified), grad_scale}: the schedule advances by rewriting it, so the launch can live in a CUDA graph. */
+int fnr_adam_step(const fnr_adam_tensor* tensors, int32_t count, int32_t kind, const float* hyper, void* stream);
 
 int fnr_version(void);
 const char* fnr_last_error(void);

@@ -1,0 +1,136 @@
+"""CPU tests of the training shell's host logic: synthetic scene, pixel batches, schedules, optimiser
+hyper-parameters (against torch.optim's own formulas), clustering."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from fruitnerf_b200 import _lib as L
+from fruitnerf_b200.clustering import count_fruits, voxel_down_sample
+from fruitnerf_b200.data.fruit_datamanager import FruitDataManagerConfig
+from fruitnerf_b200.data.synthetic_scene import camera_rays, look_at_c2w, make_apple_scene, make_geometry, trace, write_dataset
+from fruitnerf_b200.optim import ExponentialDecay, FusedAdam
+
+
+def test_scene_geometry_and_masks():
+    train, ev = make_apple_scene(num_images=20, height=48, width=48, num_fruits=6, seed=3)
+    assert len(train) == 18 and len(ev) == 2  # every 10th image is held out (train_split_fraction 0.9)
+    assert train.images.shape == (18, 48, 48, 3) and train.fruit_masks.shape == (18, 48, 48, 1)
+    assert set(train.fruit_masks.unique().tolist()) <= {0.0, 1.0}
+    assert 0.0 < float(train.fruit_masks.mean()) < 0.3
+    assert float(train.images.min()) >= 0.0 and float(train.images.max()) <= 1.0
+    # cameras inside the +/-1 scene box (auto_scale_poses), rotation part orthonormal, looking at the tree
+    c2w = train.cameras.camera_to_worlds
+    assert float(c2w[:, :, 3].abs().max()) <= 1.0
+    eye = torch.eye(3).expand(len(train), 3, 3)
+    assert torch.allclose(c2w[:, :, :3].transpose(1, 2) @ c2w[:, :, :3], eye, atol=1e-5)
+    # fruit pixels are red-dominant, the mask marks exactly the fruit hits of the tracer
+    fruit = train.fruit_masks[..., 0] > 0.5
+    assert bool((train.images[fruit][:, 0] > train.images[fruit][:, 1]).all())
+    g = train.geometry
+    d = torch.cdist(g.fruit_centers, g.fruit_centers) + 10 * torch.eye(6)
+    assert float(d.min()) > 0.14
+
+
+def test_center_pixel_ray_hits_target():
+    eye, target = torch.tensor([0.9, 0.1, 0.4]), torch.tensor([0.0, 0.0, 0.02])
+    c2w = look_at_c2w(eye, target)
+    # pixel centre (cx - 0.5) looks exactly along the optical axis
+    o, d = camera_rays(c2w, 100.0, 100.0, 32.5, 24.5, torch.tensor([24]), torch.tensor([32]))
+    want = (target - eye) / (target - eye).norm()
+    assert torch.allclose(d[0], want, atol=1e-6) and torch.allclose(o[0], eye)
+    # a ray straight at a fruit centre reports a fruit hit at distance |c - o| - r
+    geom = make_geometry(4, seed=1)
+    c = geom.fruit_centers[0]
+    o = c + torch.tensor([0.0, 0.0, 1.0])
+    rgb, mask, t = trace(geom, o[None], torch.tensor([[0.0, 0.0, -1.0]]))
+    if float(mask[0, 0]) == 1.0:  # unless a leaf blob sits above it
+        assert abs(float(t[0]) - (1.0 - geom.fruit_radius)) < 1e-5
+
+
+def test_datamanager_pixel_batches_are_consistent():
+    cfg = FruitDataManagerConfig(train_num_rays_per_batch=300, eval_num_rays_per_batch=64,
+                                 synthetic_scene=dict(num_images=10, height=24, width=32, num_fruits=3))
+    dm = cfg.setup(device="cpu")
+    rb, batch = dm.next_train(0)
+    assert rb.origins.shape == (300, 3) and rb.camera_indices.shape == (300, 1) and batch["image"].shape == (300, 3)
+    assert batch["fruit_mask"].shape == (300, 1)
+    assert torch.allclose(rb.directions.norm(dim=-1), torch.ones(300), atol=1e-6)
+    ds = dm.train_dataset
+    idx = batch["indices"]
+    assert int(idx[:, 0].max()) < len(ds) and int(idx[:, 1].max()) < 24 and int(idx[:, 2].max()) < 32
+    assert torch.equal(batch["image"], ds.images[idx[:, 0], idx[:, 1], idx[:, 2]])
+    assert torch.equal(rb.origins, ds.cameras.camera_to_worlds[idx[:, 0], :, 3])
+    # the pixel colour is what the tracer returns for that ray
+    rgb, mask, _ = trace(ds.geometry, rb.origins, rb.directions)
+    assert torch.allclose(rgb, batch["image"], atol=1e-5) and torch.equal(mask, batch["fruit_mask"])
+    rb2, _ = dm.next_train(1)
+    assert not torch.equal(rb.directions, rb2.directions)
+    i, cam_bundle, b = dm.next_eval_image(0)
+    assert cam_bundle.origins.shape == (24, 32, 3) and b["image"].shape == (24, 32, 3)
+
+
+def test_write_dataset_layout(tmp_path):
+    train, _ = make_apple_scene(num_images=5, height=16, width=16, num_fruits=2)
+    path = write_dataset(train, tmp_path / "apple")
+    import json
+
+    meta = json.loads(path.read_text())
+    assert {"fl_x", "fl_y", "cx", "cy", "w", "h", "frames"} <= set(meta)
+    fr0 = meta["frames"][0]
+    assert {"file_path", "semantic_path", "transform_matrix"} <= set(fr0)
+    from PIL import Image
+
+    m = np.array(Image.open(tmp_path / "apple" / fr0["semantic_path"]))
+    assert set(np.unique(m).tolist()) <= {0, 255}  # fruit_dataset.py:47-52 normalises by 255
+
+
+def test_exponential_decay_schedule():
+    s = ExponentialDecay(1e-2, 1e-4, 200000)
+    assert s.lr(0) == pytest.approx(1e-2) and s.lr(200000) == pytest.approx(1e-4) and s.lr(10**7) == pytest.approx(1e-4)
+    assert s.lr(100000) == pytest.approx(1e-3)
+    assert ExponentialDecay(1e-2, None, None).lr(12345) == 1e-2
+
+
+@pytest.mark.parametrize("kind", ["Adam", "RAdam"])
+def test_hyper_values_follow_torch_formulas(kind):
+    opt = FusedAdam.__new__(FusedAdam)
+    opt.kind = {"Adam": L.FNR_OPT_ADAM, "RAdam": L.FNR_OPT_RADAM}[kind]
+    opt.lr, opt.eps, opt.betas, opt.scheduler = 1e-2, 1e-15, (0.9, 0.999), ExponentialDecay(1e-2, 1e-4, 1000)
+    for step in (1, 2, 5, 6, 7, 100):
+        h = opt._hyper_values(step, 0.5)
+        assert h[0] == pytest.approx(opt.scheduler.lr(step - 1), rel=1e-6)  # LambdaLR: step k uses lambda(k-1)
+        assert h[4] == pytest.approx(1 - 0.9**step, rel=1e-6) and h[5] == pytest.approx(1 - 0.999**step, rel=1e-5)
+        assert h[7] == 0.5
+        if kind == "RAdam":
+            rho_inf = 2 / (1 - 0.999) - 1
+            rho_t = rho_inf - 2 * step * 0.999**step / (1 - 0.999**step)
+            if rho_t > 5:
+                want = math.sqrt((rho_t - 4) * (rho_t - 2) * rho_inf / ((rho_inf - 4) * (rho_inf - 2) * rho_t))
+                assert h[6] == pytest.approx(want, rel=1e-5)
+            else:
+                assert h[6] < 0
+        else:
+            assert h[6] < 0
+
+
+def test_fused_adam_refuses_cpu_parameters():
+    with pytest.raises(L.FruitNerfNativeError):
+        FusedAdam([torch.zeros(4)])
+
+
+def test_clustering_counts_blobs_and_merges_fragments():
+    rng = np.random.default_rng(0)
+    centers = np.array([[0, 0, 0], [0.5, 0, 0], [0, 0.5, 0.2], [0.4, 0.4, 0.4]], dtype=float)
+    pts = np.concatenate([c + 0.02 * rng.standard_normal((400, 3)) for c in centers])
+    # a small fragment 0.05 away from blob 0 (what DBSCAN splits off a fruit): merged by the centre-distance rule
+    frag = centers[0] + np.array([0.05, 0, 0]) + 0.004 * rng.standard_normal((60, 3))
+    noise = rng.uniform(-1, 1, (30, 3))
+    res = count_fruits(np.concatenate([pts, frag, noise]), eps=0.012, min_samples=8, cluster_merge_distance=0.08)
+    assert res["count"] == 4 and res["count_before_merge"] >= 4
+    d = np.linalg.norm(res["centers"][:, None] - centers[None], axis=-1).min(axis=0)
+    assert d.max() < 0.03
+    assert count_fruits(np.zeros((0, 3)), 0.1, 5, 0.1)["count"] == 0
+    ds = voxel_down_sample(np.array([[0.0, 0, 0], [0.01, 0, 0], [1.0, 1, 1]]), 0.1)
+    assert ds.shape == (2, 3)
