@@ -178,7 +178,7 @@ class SyntheticFruitDataset:
 
 
 def make_apple_scene(num_images: int = 40, height: int = 160, width: int = 160, num_fruits: int = 12, seed: int = 0, radius: float = 1.0,
-                     device="cpu") -> Tuple[SyntheticFruitDataset, SyntheticFruitDataset]:
+                     elevations=(12.0, 30.0, 50.0), device="cpu") -> Tuple[SyntheticFruitDataset, SyntheticFruitDataset]:
     """(train, eval) data sets of the synthetic apple tree.  Cameras orbit at ``radius`` (inside the +/-1 box after the
     dataparser's auto-scaling) on three elevation rings; every 10th image goes to the eval split (train_split_fraction 0.9)."""
     geom = make_geometry(num_fruits, seed)
@@ -186,7 +186,7 @@ def make_apple_scene(num_images: int = 40, height: int = 160, width: int = 160, 
     poses = []
     for i in range(num_images):
         az = 2 * math.pi * i / num_images + 0.37 * (i % 3)
-        el = math.radians((12.0, 30.0, 50.0)[i % 3])
+        el = math.radians(elevations[i % len(elevations)])
         eye = target + radius * torch.tensor([math.cos(az) * math.cos(el), math.sin(az) * math.cos(el), math.sin(el)])
         poses.append(look_at_c2w(eye, target))
     c2w = torch.stack(poses).to(torch.float32)

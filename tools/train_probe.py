@@ -8,7 +8,10 @@ from fruitnerf_b200.trainer import Trainer
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 prof_at = int(sys.argv[2]) if len(sys.argv) > 2 else steps
 torch.manual_seed(0)
-tr = Trainer(synthetic_spec("fruit_nerf"), device="cuda:0", use_cuda_graph=os.environ.get("NO_GRAPH") is None)
+spec = synthetic_spec("fruit_nerf", num_images=int(os.environ.get("NIMG", 40)))
+if os.environ.get("ELEV"):
+    spec.pipeline.datamanager.synthetic_scene["elevations"] = tuple(float(v) for v in os.environ["ELEV"].split(","))
+tr = Trainer(spec, device="cuda:0", use_cuda_graph=os.environ.get("NO_GRAPH") is None)
 model = tr.pipeline.model
 
 
