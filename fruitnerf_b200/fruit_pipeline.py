@@ -66,6 +66,7 @@ class FruitPipeline(nn.Module):
         )
         self._model.to(device)
         self.world_size = world_size
+        self.local_rank = local_rank
         if world_size > 1:
             dist.barrier()  # fruit_pipeline.py:118
 

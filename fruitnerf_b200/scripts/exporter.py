@@ -44,10 +44,19 @@ class ExportSemanticPointCloud(Exporter):
             with open(Path(self.load_config).parent / "dataparser_transforms.json", "r") as fp:
                 transform_json = json.load(fp)
         pcds = sample_volume(pipeline=pipeline, num_points=num_points, output_dir=self.output_dir, config=config,
-                             transform_json=transform_json)
+                             transform_json=transform_json, world_size=getattr(pipeline, "world_size", 1),
+                             rank=getattr(pipeline, "local_rank", 0))
         for name, pcd in pcds.items():
             path = pcd["path"] or str(self.output_dir / f"{name}.ply")
             os.makedirs(os.path.dirname(path), exist_ok=True)
             write_ply(path, pcd["points"], pcd["colors"])
             pcd["path"] = path
         return pcds
+
+
+def entrypoint():
+    """``ns-export-semantics`` (exporter.py:124-144 upstream parses the sub-command with tyro and calls ``main``).
+    Building the pipeline from a nerfstudio YAML config (``eval_setup``) is control plane and not rebuilt: use
+    ``ExportSemanticPointCloud(load_config=None, output_dir=...).main(pipeline=...)`` from Python."""
+    raise SystemExit("ns-export-semantics: construct a FruitPipeline(test_mode='export') and call "
+                     "ExportSemanticPointCloud(...).main(pipeline=pipeline); nerfstudio's eval_setup is out of scope")

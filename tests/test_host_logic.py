@@ -154,6 +154,19 @@ own = torch.arange(rank * R, (rank + 1) * R)
 allr = [torch.zeros(R, dtype=torch.long) for _ in range(world)]
 dist.all_gather(allr, own)
 assert torch.equal(torch.cat(allr), torch.arange(world * R))
+# export sharding: contiguous slabs cover the ray grid once; merged point lists are identical on every rank
+from fruitnerf_b200.export.exporter_utils import export_slab, merge_export_shards
+N = 1001
+slabs = [export_slab(N, world, r) for r in range(world)]
+assert slabs[0][0] == 0 and slabs[-1][1] == N and all(slabs[i][1] == slabs[i + 1][0] for i in range(world - 1))
+lo, hi = slabs[rank]
+keys = torch.arange(lo, hi, dtype=torch.int64)[::7]
+rows = torch.stack([keys.float() * k for k in range(7)], dim=1)
+merged = merge_export_shards({"density": (rows, keys)}, world)
+mk = merged["density"][1]
+want = torch.cat([torch.arange(*export_slab(N, world, r), dtype=torch.int64)[::7] for r in range(world)])
+assert torch.equal(torch.sort(mk).values, torch.sort(want).values)
+assert torch.equal(merged["density"][0][:, 1].long(), mk)
 dist.barrier()
 print("rank", rank, "ok")
 """

@@ -5,6 +5,8 @@ hand / by independent integer arithmetic from the formulas the reference's depen
 """
 from pathlib import Path
 
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -213,3 +215,83 @@ def test_oracle_gradients_match_finite_differences():
     f = fr.field_forward(st, spec, o[:, None, :], d[:, None, :], s[..., None], e[..., None], cam, True, "train")
     r = fr.render(f, s[..., None], e[..., None], training=True)
     assert not r["semantics"].sum().requires_grad or torch.autograd.grad(r["semantics"].sum(), st["mlp_base_mlp.layers.0.weight"], allow_unused=True)[0] is None
+
+
+# ---- golden vectors of the proposal stage / compositing edge cases / gradients -------------------------------------
+def _gold(name):
+    return {k: v for k, v in np.load(GOLD / name).items()}
+
+
+def test_proposal_stage_golden():
+    g = _gold("proposal.npz")
+    R = g["origins"].shape[0]
+    aabb = torch.tensor([[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]])
+    sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd_")}
+    spec = fr.DensitySpec(num_levels=5, max_res=128, log2_hashmap_size=12)
+    o, d = torch.from_numpy(g["origins"]), torch.from_numpy(g["directions"])
+    nears, fars = torch.full((R, 1), 0.05), torch.full((R, 1), 1000.0)
+    bins = torch.from_numpy(g["bins0"])
+    e = ns.spacing_to_euclidean(bins, nears, fars)
+    assert np.array_equal(e.numpy(), g["euclid0"])
+    # piecewise map: linear below distance 1 (s = x/2), linear in disparity beyond; monotone, inside [near, far]
+    # (the stratified jitter also moves the outermost edges inwards)
+    assert bool((e[:, 0] >= 0.05).all()) and bool((e[:, -1] <= 1000.0 * (1 + 1e-6)).all())
+    det = ns.spacing_to_euclidean(ns.spaced_bins(1, 64, None), nears[:1], fars[:1])
+    assert float(det[0, 0]) == pytest.approx(0.05) and float(det[0, -1]) == pytest.approx(1000.0, rel=1e-4)
+    assert bool((e[:, 1:] >= e[:, :-1]).all())
+    w = fr.proposal_weights(sd, spec, o, d, e[:, :-1], e[:, 1:], aabb)
+    assert np.allclose(w.numpy(), g["weights0"], rtol=1e-6, atol=1e-9)
+    w_zero = w.clone()
+    w_zero[0] = 0.0
+    for tag, anneal in (("eval", 1.0), ("single", 0.37), ("perbin", 1.0)):
+        u = torch.from_numpy(g[f"pdf_{tag}_u"]) if f"pdf_{tag}_u" in g else None
+        nb = ns.pdf_sample(torch.pow(w_zero, anneal), bins, 24, u)
+        assert np.allclose(nb.numpy(), g[f"pdf_{tag}_bins"], rtol=0, atol=1e-7), tag
+        assert bool((nb[:, 1:] >= nb[:, :-1]).all()) and float(nb.min()) >= 0.0 and float(nb.max()) <= 1.0
+    # an all-zero histogram (ray 0) resamples uniformly over the existing bins' span
+    nb0 = torch.from_numpy(g["pdf_eval_bins"])[0]
+    assert torch.allclose(nb0[1:] - nb0[:-1], (nb0[1:] - nb0[:-1]).mean().expand(24), atol=2e-3)
+    nb = torch.from_numpy(g["pdf_eval_bins"])
+    w2 = torch.from_numpy(g["weights1"])
+    assert float(ns.interlevel_loss([w, w2], [bins, nb])) == pytest.approx(float(g["interlevel"]), rel=1e-6)
+    outer = ns.lossfun_outer(nb, w2, bins, w)
+    assert np.allclose(outer.numpy(), g["outer"], rtol=1e-5, atol=1e-9) and float(outer.min()) >= 0.0
+
+
+def test_compositing_edge_case_golden():
+    g = _gold("composite_gradients.npz")
+    dens, rgb, sem = (torch.from_numpy(g[k]) for k in ("c_density", "c_rgb", "c_semantics"))
+    starts = torch.arange(4, dtype=torch.float32).expand(5, 4)[..., None]
+    r = fr.render({"density": dens, "rgb": rgb, "semantics": sem}, starts, starts + 1.0, training=False)
+    for k in ("rgb", "accumulation", "depth", "semantics", "weights"):
+        assert np.allclose(r[k].numpy(), g[f"c_out_{k}"], rtol=1e-6, atol=1e-7, equal_nan=False), k
+    assert np.array_equal(r["depth_index"].numpy(), g["c_out_depth_index"])
+    w = r["weights"][..., 0]
+    # hand-derived: sigma = 0 -> no weight, colour = last sample; opaque first sample takes everything;
+    # NaN density: that sample and everything behind it contribute 0 (nan_to_num); ln2 then opaque: 0.5 / 0.5 tie -> index 0
+    assert torch.equal(w[0], torch.zeros(4)) and torch.allclose(r["rgb"][0], rgb[0, -1])
+    assert torch.allclose(w[1], torch.tensor([1.0, 0.0, 0.0, 0.0]))
+    assert torch.allclose(w[2], torch.tensor([1 - math.exp(-0.5), 0.0, 0.0, 0.0]), atol=1e-7)
+    assert torch.allclose(w[3], torch.tensor([0.5, 0.5, 0.0, 0.0]), atol=1e-7) and int(r["depth_index"][3]) == 0
+    assert bool(torch.isfinite(r["rgb"]).all())
+
+
+def test_gradient_golden_is_reproducible():
+    g = _gold("composite_gradients.npz")
+    v = syn.SMALL
+    sd = syn.field_state(geo=v["geo"], sem_dims=v["sem_dims"], log2_hashmap_size=12, num_images=3, table_scale=0.5, weight_gain=1.5)
+    spec = fr.FieldSpec(max_res=v["max_res"], log2_hashmap_size=12, geo_feat_dim=v["geo"])
+    o, d, s, e, cam = syn.ray_batch(16, 12, salt=931, far=3.0, num_images=3)
+    img, mask = syn.targets(16, salt=932)
+    sdg = {k: t.clone().requires_grad_(k != "aabb") for k, t in sd.items()}
+    f = fr.field_forward(sdg, spec, o[:, None, :], d[:, None, :], s[..., None], e[..., None], cam, True, "train")
+    loss = sum(fr.loss_dict(fr.render(f, s[..., None], e[..., None], training=True), img, mask).values())
+    loss.backward()
+    assert float(loss) == pytest.approx(float(g["g_loss"]), rel=1e-6)
+    for k in g:
+        if k.startswith("g_") and k not in ("g_loss", "g_table_rows", "g_table_vals"):
+            ref = g[k]
+            assert np.allclose(sdg[k[2:]].grad.numpy(), ref, rtol=1e-4, atol=1e-6 * np.abs(ref).max()), k
+    assert np.allclose(sdg["mlp_base_grid.hash_table"].grad[torch.from_numpy(g["g_table_rows"])].numpy(), g["g_table_vals"], rtol=1e-4,
+                       atol=1e-6 * np.abs(g["g_table_vals"]).max())
+    # the semantic branch is detached from the geometry features (fruit_field.py:264-265): the colour loss alone reaches the base MLP
