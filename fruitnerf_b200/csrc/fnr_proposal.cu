@@ -124,9 +124,12 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) proposal_weights_forward_
         x = (en - st) * sigma;
       }
       const float incl = warp_incl_scan(x, lane);
+      // exclusive prefix by shuffle, not `incl - x`: an infinite sigma*delta must give T = 1 in front of it (torch.cumsum semantics)
+      float excl = __shfl_up_sync(kFull, incl, 1);
+      if (lane == 0) excl = 0.f;
       if (in) {
         const float alpha = 1.0f - expf(-x);
-        const float T = expf(-(run_x + (incl - x)));
+        const float T = expf(-(run_x + excl));
         weights[base + i] = nan_to_num(alpha * T);
       }
       run_x += __shfl_sync(kFull, incl, 31);

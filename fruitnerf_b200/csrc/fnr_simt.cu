@@ -276,9 +276,12 @@ __global__ void __launch_bounds__(kThreads) simt_composite_kernel(KRays Rr, KCom
         x = delta * Cm.sample_density[base + i];
       }
       const float incl = warp_incl_scan(x, lane);
+      // exclusive prefix by shuffle, not `incl - x`: an infinite sigma*delta must give T = 1 in front of it (torch.cumsum semantics)
+      float excl = __shfl_up_sync(kFull, incl, 1);
+      if (lane == 0) excl = 0.f;
       if (in) {
         const float alpha = 1.0f - expf(-x);
-        const float T = expf(-(run_x + (incl - x)));
+        const float T = expf(-(run_x + excl));
         w = nan_to_num(alpha * T);
         if (Cm.weights) Cm.weights[base + i] = w;
         float c0r = Cm.sample_rgb[3 * (base + i)], c0g = Cm.sample_rgb[3 * (base + i) + 1], c0b = Cm.sample_rgb[3 * (base + i) + 2];

@@ -497,9 +497,12 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
           float x = 0.f, w = 0.f;
           if (in) x = (a.Rr.ends[base + i] - a.Rr.starts[base + i]) * sp[5 * i];
           const float incl = warp_incl_scan_f(x, lane);
+          // exclusive prefix by shuffle, not `incl - x`: an infinite sigma*delta must give T = 1 in front of it (torch.cumsum semantics)
+          float excl = __shfl_up_sync(kFullMask, incl, 1);
+          if (lane == 0) excl = 0.f;
           if (in) {
             const float alpha = 1.0f - expf(-x);
-            const float T = expf(-(run_x + (incl - x)));
+            const float T = expf(-(run_x + excl));
             w = nan_to_num(alpha * T);
             if (Cm.weights) Cm.weights[base + i] = w;
             float c0r = sp[5 * i + 1], c0g = sp[5 * i + 2], c0b = sp[5 * i + 3];

@@ -178,7 +178,7 @@ class SyntheticFruitDataset:
 
 
 def make_apple_scene(num_images: int = 40, height: int = 160, width: int = 160, num_fruits: int = 12, seed: int = 0, radius: float = 1.0,
-                     elevations=(12.0, 30.0, 50.0), device="cpu") -> Tuple[SyntheticFruitDataset, SyntheticFruitDataset]:
+                     elevations=(12.0, 30.0, 50.0), noise_std: float = 0.02, device="cpu") -> Tuple[SyntheticFruitDataset, SyntheticFruitDataset]:
     """(train, eval) data sets of the synthetic apple tree.  Cameras orbit at ``radius`` (inside the +/-1 box after the
     dataparser's auto-scaling) on three elevation rings; every 10th image goes to the eval split (train_split_fraction 0.9)."""
     geom = make_geometry(num_fruits, seed)
@@ -199,6 +199,11 @@ def make_apple_scene(num_images: int = 40, height: int = 160, width: int = 160, 
         imgs.append(rgb.reshape(height, width, 3))
         masks.append(m.reshape(height, width, 1))
     images, fruit_masks = torch.stack(imgs), torch.stack(masks)
+    if noise_std > 0:
+        # sensor noise: photographs never let the photometric loss reach zero; a noise-free render does, and Adam with
+        # eps = 1e-15 at a constant 1e-2 learning rate then amplifies round-off-level gradients
+        gn = torch.Generator().manual_seed(seed + 12345)
+        images = (images + noise_std * torch.randn(images.shape, generator=gn).to(images.device)).clamp(0.0, 1.0)
     scene_box = SceneBox(aabb=torch.tensor([[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]], dtype=torch.float32))
     idx = torch.arange(num_images)
     eval_idx = idx[idx % 10 == 9]

@@ -152,6 +152,29 @@ def test_render_eval_clamp_and_composite_edge_cases(native_lib, cuda_device):
     assert float(out["rgb"].min()) >= 0.0 and float(out["rgb"].max()) <= 1.0
 
 
+@pytest.mark.parametrize("impl", IMPLS, ids=IMPL_IDS)
+def test_infinite_density_keeps_the_first_sample(native_lib, cuda_device, impl):
+    """trunc_exp overflow (h0 > 88.7 -> sigma = +inf): torch's get_weights gives weight 1 to the first such sample (T = 1 in
+    front of it, alpha = 1) and 0 behind it -- not NaN -> 0 everywhere, which would silence the whole ray."""
+    sd, spec = make_state("small")
+    sd = dict(sd)
+    sd["mlp_base_mlp.layers.1.bias"] = sd["mlp_base_mlp.layers.1.bias"].clone()
+    sd["mlp_base_mlp.layers.1.bias"][0] = 120.0
+    field = make_field("small", sd, spec, cuda_device).eval()
+    o, d, s, e, cam = _rays(32, 48, salt=9, far=2.0)
+    with torch.no_grad():
+        out = _render_gpu(field, o, d, s, e, None, impl, clamp=True)
+    f = _oracle_field(sd, spec, o, d, s, e, None, True, "zeros")
+    ref = fr.render(f, s[..., None], e[..., None], training=False)
+    assert bool(torch.isinf(f["density"]).any())
+    w = out["weights"].cpu()
+    assert torch.equal(w, ref["weights"][..., 0]) or torch.allclose(w, ref["weights"][..., 0], atol=1e-6)
+    inside = torch.isinf(f["density"][:, 0, 0])  # rays whose first sample is inside the box (selector = 1)
+    assert bool(inside.any()) and bool((w[inside, 0] == 1.0).all()) and bool((w[inside, 1:] == 0.0).all())
+    assert_rel(out["rgb"], ref["rgb"], what="rgb")
+    assert_rel(out["accumulation"], ref["accumulation"][..., 0], what="accumulation")
+
+
 RELU_MARGIN = 1e-4  # samples with a hidden pre-activation within 1e-4 (relative to the layer rms) of zero
 
 

@@ -33,6 +33,15 @@ def test_scene_geometry_and_masks():
     assert float(d.min()) > 0.14
 
 
+def test_sensor_noise_is_seeded_and_bounded():
+    a, _ = make_apple_scene(num_images=5, height=16, width=16, num_fruits=2, seed=1, noise_std=0.02)
+    b, _ = make_apple_scene(num_images=5, height=16, width=16, num_fruits=2, seed=1, noise_std=0.02)
+    clean, _ = make_apple_scene(num_images=5, height=16, width=16, num_fruits=2, seed=1, noise_std=0.0)
+    assert torch.equal(a.images, b.images) and torch.equal(a.fruit_masks, clean.fruit_masks)
+    assert float(a.images.min()) >= 0.0 and float(a.images.max()) <= 1.0
+    assert 0.01 < float((a.images - clean.images).std()) < 0.025
+
+
 def test_center_pixel_ray_hits_target():
     eye, target = torch.tensor([0.9, 0.1, 0.4]), torch.tensor([0.0, 0.0, 0.02])
     c2w = look_at_c2w(eye, target)
@@ -51,7 +60,7 @@ def test_center_pixel_ray_hits_target():
 
 def test_datamanager_pixel_batches_are_consistent():
     cfg = FruitDataManagerConfig(train_num_rays_per_batch=300, eval_num_rays_per_batch=64,
-                                 synthetic_scene=dict(num_images=10, height=24, width=32, num_fruits=3))
+                                 synthetic_scene=dict(num_images=10, height=24, width=32, num_fruits=3, noise_std=0.0))
     dm = cfg.setup(device="cpu")
     rb, batch = dm.next_train(0)
     assert rb.origins.shape == (300, 3) and rb.camera_indices.shape == (300, 1) and batch["image"].shape == (300, 3)
