@@ -262,6 +262,9 @@ def run_ours(args):
     fwd_ach = fwd_bytes / (mean_fwd * 1e-3) / 1e9
     bwd_ach = bwd_bytes / (mean_bwd * 1e-3) / 1e9
     dominant_is_bwd = mean_bwd >= mean_fwd
+    on_tc = args.variant == "small" and args.kernel != "simt"  # the families the tcgen05 kernels serve (fnr_api.cu dispatch)
+    fwd_kernel = "tc_render_forward_kernel" if on_tc else "simt_field_forward_kernel + simt_composite_kernel"
+    bwd_kernel = "tc_field_backward_kernel" if on_tc else "simt_field_backward_kernel"
     line = {
         "metric": "rays/sec (4096 rays x 192 samples) fused fwd+bwd",
         "value": world * R_RAYS * args.steps / (total_ms * 1e-3),
@@ -290,19 +293,21 @@ def run_ours(args):
         "bwd_ms": mean_bwd,
         "fwd_rays_per_s": R_RAYS / (mean_fwd * 1e-3),
         "roofline": {
-            "kernel": ("render backward (tc_field_backward_kernel + composite backward + loss)" if dominant_is_bwd
-                       else "fused render forward (tc_render_forward_kernel)"),
+            "kernel": (f"render backward ({bwd_kernel} + simt_composite_backward_kernel + loss)" if dominant_is_bwd
+                       else f"fused render forward ({fwd_kernel})"),
             "bound": "hbm",
             "achieved": bwd_ach if dominant_is_bwd else fwd_ach,
             "peak": peak,
             "unit": "GB/s",
             "frac": (bwd_ach if dominant_is_bwd else fwd_ach) / peak,
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+            # `ncu --set full` capture (profiles/r1_ncu_summary.md, final round-1 tables); small variant only
+            "traffic": (NCU_DRAM_BYTES["bwd" if dominant_is_bwd else "fwd"] if on_tc else None),
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": bwd_bytes if dominant_is_bwd else fwd_bytes,
             "launch_ms": mean_bwd if dominant_is_bwd else mean_fwd,
         },
-        "roofline_forward": {"kernel": "tc_render_forward_kernel", "bound": "hbm", "achieved": fwd_ach, "peak": peak, "unit": "GB/s",
+        "roofline_forward": {"kernel": fwd_kernel, "bound": "hbm", "achieved": fwd_ach, "peak": peak, "unit": "GB/s",
                              "frac": fwd_ach / peak, "launch_ms": mean_fwd, "algorithmic_bytes_per_launch": fwd_bytes},
         "roofline_step": {"bound": "hbm", "achieved": (fwd_bytes + bwd_bytes) / (mean_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                           "frac": (fwd_bytes + bwd_bytes) / (mean_step * 1e-3) / 1e9 / peak},
@@ -314,6 +319,12 @@ def run_ours(args):
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args.variant, sample_rays=args.cpu_rays, repeats=1)
     print(json.dumps(line))
+
+
+# per-launch DRAM traffic measured by ncu (profiles/r1_ncu_summary.md): tc_render_forward_kernel 57.9 MB read + 87.2 MB
+# written; tc_field_backward_kernel 176.9 MB read + 19.7 MB written.  Far below the algorithmic hash bytes because the
+# 64 MiB fruit_nerf table is L2-resident.
+NCU_DRAM_BYTES = {"fwd": 57_898_240 + 87_247_360, "bwd": 176_867_840 + 19_650_816}
 
 
 def cpu_baseline(variant: str, sample_rays: int, repeats: int):

@@ -185,12 +185,15 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    import os
+
+    path = Path(os.environ.get("FNR_LIB") or LIB_PATH)  # FNR_LIB: load an experimental build of the same ABI (tools/ only)
+    if not path.exists():
         raise FruitNerfNativeError(
-            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a).  fruitnerf_b200 has no CPU / PyTorch fallback."
         )
-    lib = C.CDLL(str(LIB_PATH))
+    lib = C.CDLL(str(path))
     lib.fnr_version.restype = C.c_int
     lib.fnr_last_error.restype = C.c_char_p
     lib.fnr_render_forward.restype = C.c_int

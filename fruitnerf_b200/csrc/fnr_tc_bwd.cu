@@ -165,7 +165,10 @@ __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.al
 template <int N>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 constexpr int BAR_COMPUTE = 1, BAR_FULL = 2, BAR_EMPTY = 3;
-constexpr int kAggLevels = 4;  // coarse levels whose reds are run-length aggregated across the warp
+#ifndef FNR_AGG_LEVELS
+#define FNR_AGG_LEVELS 4
+#endif
+constexpr int kAggLevels = FNR_AGG_LEVELS;  // coarse levels whose reds are run-length aggregated across the warp
 
 struct BwdArgs {
   KField F;
