@@ -60,22 +60,23 @@ class Trainer:
             if cb["where_to_run"] == where and step % cb.get("update_every_num_iters", 1) == 0:
                 cb["func"](step)
 
-    def _exchange(self, params) -> None:
+    def _exchange(self, grads) -> None:
         """Mean of the gradients over ranks (the reference wraps the model in DDP, fruit_pipeline.py:117).  Field
         gradients are views of one flat buffer: a single collective; other groups are coalesced first."""
-        grads = [p.grad for p in params]
-        base = grads[0]._base if grads[0]._base is not None else None
+        from .fruit_pipeline import sync_gradients
+
+        base = grads[0]._base
         if base is not None and all(g._base is base for g in grads):
-            dist.all_reduce(base, op=dist.ReduceOp.AVG)
+            sync_gradients(base, self.world_size)
             return
         flat = torch.cat([g.reshape(-1) for g in grads])
-        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        sync_gradients(flat, self.world_size)
         off = 0
         for g in grads:
             g.copy_(flat[off:off + g.numel()].view_as(g))
             off += g.numel()
 
-    def _device_work(self, step: int, launch_only: bool):
+    def _device_work(self, step: int, launch_only: bool, with_optimizer: bool = True):
         """Everything an iteration enqueues on the GPU (this is what a CUDA graph captures)."""
         for params in self.param_groups.values():
             for p in params:
@@ -83,21 +84,25 @@ class Trainer:
         _, loss_dict, metrics_dict = self.pipeline.get_train_loss_dict(step)
         loss = sum(loss_dict.values())
         loss.backward()
+        if with_optimizer:
+            self._exchange_and_step({name: [p.grad for p in params] for name, params in self.param_groups.items()}, launch_only)
+        # detached: nothing may keep the autograd graph (and its AccumulateGrad nodes, which remember their stream) alive
+        # across iterations -- a later CUDA-graph capture runs on a different stream
+        return loss.detach(), {k: v.detach() for k, v in loss_dict.items()}, {k: v.detach() for k, v in metrics_dict.items()}
+
+    def _exchange_and_step(self, grads_by_group: Dict[str, list], launch_only: bool) -> None:
         for name, opt in self.optimizers.items():
-            params = self.param_groups[name]
-            if any(p.grad is None for p in params):
+            grads = grads_by_group[name]
+            if any(g is None for g in grads):
                 # torch optimisers skip parameters without a gradient: the proposal networks on the iterations the
                 # sampler runs them under no_grad (update_sched, fruit_nerf.py:131-136)
                 continue
             if self.world_size > 1:
-                self._exchange(params)
+                self._exchange(grads)
             if launch_only:
-                opt.launch()
+                opt.launch(grads)
             else:
-                opt.step()
-        # detached: nothing may keep the autograd graph (and its AccumulateGrad nodes, which remember their stream) alive
-        # across iterations -- a later CUDA-graph capture runs on a different stream
-        return loss.detach(), {k: v.detach() for k, v in loss_dict.items()}, {k: v.detach() for k, v in metrics_dict.items()}
+                opt.step(grads)
 
     def train_iteration(self, step: int):
         self._run_callbacks("BEFORE_TRAIN_ITERATION", step)
@@ -125,14 +130,20 @@ class Trainer:
                 if updated not in self._graphs:
                     counters = (self.pipeline.datamanager.train_count, sampler._steps_since_update if sampler is not None else 0)
                     graph = torch.cuda.CUDAGraph()
+                    # multi-GPU: the collective and the optimiser launches stay outside the graph (NCCL inside a captured
+                    # region deadlocked on this stack); single GPU: the whole iteration is one graph
+                    in_graph_opt = self.world_size == 1
                     with torch.cuda.graph(graph):
-                        captured = self._device_work(step, launch_only=True)
-                    self._graphs[updated] = (graph, captured)
+                        captured = self._device_work(step, launch_only=True, with_optimizer=in_graph_opt)
+                    grads = None if in_graph_opt else {name: [p.grad for p in params] for name, params in self.param_groups.items()}
+                    self._graphs[updated] = (graph, captured, grads)
                     self.pipeline.datamanager.train_count = counters[0]  # capture ran the Python side once without executing
                     if sampler is not None:
                         sampler._steps_since_update = counters[1]
-                graph, result = self._graphs[updated]
+                graph, result, static_grads = self._graphs[updated]
                 graph.replay()
+                if static_grads is not None:
+                    self._exchange_and_step(static_grads, launch_only=True)
                 self.pipeline.datamanager.train_count += 1
                 if sampler is not None and updated:
                     sampler._steps_since_update = 0

@@ -154,6 +154,17 @@ own = torch.arange(rank * R, (rank + 1) * R)
 allr = [torch.zeros(R, dtype=torch.long) for _ in range(world)]
 dist.all_gather(allr, own)
 assert torch.equal(torch.cat(allr), torch.arange(world * R))
+# trainer gradient exchange: views of one flat buffer -> one collective; unrelated tensors -> coalesced
+from fruitnerf_b200.trainer import Trainer
+class _T:
+    world_size = world
+flat = torch.arange(10.0) * (rank + 1)
+views = [flat[:4].view(2, 2), flat[4:10]]
+Trainer._exchange(_T(), views)
+assert torch.allclose(flat, torch.arange(10.0) * (sum(range(1, world + 1)) / world))
+loose = [torch.full((3,), float(rank)), torch.full((2, 2), 10.0 * rank)]
+Trainer._exchange(_T(), loose)
+assert torch.allclose(loose[0], torch.full((3,), (world - 1) / 2)) and torch.allclose(loose[1], torch.full((2, 2), 10.0 * (world - 1) / 2))
 # export sharding: contiguous slabs cover the ray grid once; merged point lists are identical on every rank
 from fruitnerf_b200.export.exporter_utils import export_slab, merge_export_shards
 N = 1001
