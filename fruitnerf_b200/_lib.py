@@ -14,6 +14,7 @@ FNR_MAX_LAYERS = 4
 FNR_POS_CONTRACT, FNR_POS_AABB = 0, 1
 FNR_APP_PER_CAMERA, FNR_APP_MEAN, FNR_APP_ZEROS = 0, 1, 2
 FNR_IMPL_AUTO, FNR_IMPL_SIMT, FNR_IMPL_TCGEN05 = 0, 1, 2
+FNR_SPACING_UNIFORM, FNR_SPACING_LINDISP_PIECEWISE = 0, 1
 
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
@@ -171,6 +172,10 @@ EXPORTED_SYMBOLS = (
     "fnr_pdf_sample",
     "fnr_interlevel_loss",
     "fnr_adam_step",
+    "fnr_pixel_batch",
+    "fnr_spaced_bins",
+    "fnr_render_losses",
+    "fnr_ray_metrics",
 )
 
 _lib = None
@@ -225,6 +230,15 @@ def load() -> C.CDLL:
                                         C.c_void_p, C.c_void_p]
     lib.fnr_adam_step.restype = C.c_int
     lib.fnr_adam_step.argtypes = [C.POINTER(AdamTensor), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    vp, i32, f32 = C.c_void_p, C.c_int32, C.c_float
+    lib.fnr_pixel_batch.restype = C.c_int
+    lib.fnr_pixel_batch.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, f32, f32, f32, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.fnr_spaced_bins.restype = C.c_int
+    lib.fnr_spaced_bins.argtypes = [vp, vp, i32, vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.fnr_render_losses.restype = C.c_int
+    lib.fnr_render_losses.argtypes = [vp, vp, vp, vp, i32, f32, vp, vp, vp, vp]
+    lib.fnr_ray_metrics.restype = C.c_int
+    lib.fnr_ray_metrics.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp]
     if lib.fnr_version() != 1:
         raise FruitNerfNativeError(f"ABI version mismatch: library reports {lib.fnr_version()}")
     _lib = lib

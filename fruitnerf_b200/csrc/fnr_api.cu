@@ -490,4 +490,49 @@ int fnr_adam_step(const fnr_adam_tensor* tensors, int32_t count, int32_t kind, c
   return launch_adam(A, kind == FNR_OPT_RADAM, hyper, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int fnr_pixel_batch(const float* rand, const float* c2w, const float* images, const float* masks, int32_t num_images, int32_t height,
+                    int32_t width, float fx, float fy, float cx, float cy, int32_t num_rays, float* origins, float* directions,
+                    int32_t* camera_indices, int64_t* indices, float* image, float* fruit_mask, void* stream) {
+  if (num_rays < 0 || num_images < 1 || height < 1 || width < 1 ||
+      (num_rays > 0 && (!rand || !c2w || !images || !masks || !origins || !directions || !camera_indices || !image || !fruit_mask))) {
+    set_error("invalid arguments to fnr_pixel_batch");
+    return FNR_ERR_INVALID_ARGUMENT;
+  }
+  KPixelBatch A{num_rays, num_images, height, width, fx, fy, cx, cy, rand, c2w, images, masks, origins, directions, camera_indices, indices,
+                image, fruit_mask};
+  return launch_pixel_batch(A, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fnr_spaced_bins(const float* base_bins, const float* t_rand, int32_t t_stride, const float* nears, const float* fars, int32_t num_rays,
+                    int32_t num_samples, int32_t mode, float* bins, float* starts, float* ends, void* stream) {
+  if (num_rays < 0 || num_samples < 1 || (mode != FNR_SPACING_UNIFORM && mode != FNR_SPACING_LINDISP_PIECEWISE) ||
+      (t_rand && t_stride != 1 && t_stride != num_samples + 1) || (num_rays > 0 && (!base_bins || !nears || !fars || !bins || !starts || !ends))) {
+    set_error("invalid arguments to fnr_spaced_bins");
+    return FNR_ERR_INVALID_ARGUMENT;
+  }
+  KSpacedBins A{num_rays, num_samples, mode, base_bins, t_rand, t_stride, nears, fars, bins, starts, ends};
+  return launch_spaced_bins(A, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fnr_render_losses(const float* rgb, const float* semantics, const float* image, const float* fruit_mask, int32_t num_rays,
+                      float semantic_weight, float* out, float* d_rgb, float* d_semantics, void* stream) {
+  if (num_rays < 1 || !rgb || !semantics || !image || !fruit_mask || !out) {
+    set_error("invalid arguments to fnr_render_losses");
+    return FNR_ERR_INVALID_ARGUMENT;
+  }
+  KLosses A{num_rays, semantic_weight, rgb, semantics, image, fruit_mask, out, d_rgb, d_semantics};
+  return launch_render_losses(A, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fnr_ray_metrics(const float* weights, const float* sdist, const float* starts, const float* ends, int32_t num_rays, int32_t num_samples,
+                    float* distortion, float* median_depth, void* stream) {
+  if (num_rays < 0 || num_samples < 1 || num_samples > 4096 || (num_rays > 0 && !weights) || (distortion && !sdist) ||
+      (median_depth && (!starts || !ends))) {
+    set_error("invalid arguments to fnr_ray_metrics");
+    return FNR_ERR_INVALID_ARGUMENT;
+  }
+  KRayMetrics A{num_rays, num_samples, weights, sdist, starts, ends, distortion, median_depth};
+  return launch_ray_metrics(A, reinterpret_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

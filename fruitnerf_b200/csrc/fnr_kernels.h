@@ -97,6 +97,57 @@ struct KExport {
   int64_t* semantics_colormap;
 };
 
+// ---- per-ray glue kernels (fnr_glue.cu) ----
+struct KPixelBatch {
+  int R, N, H, W;
+  float fx, fy, cx, cy;
+  const float* rand;     // [R,3] uniform draws
+  const float* c2w;      // [N,3,4]
+  const float* images;   // [N,H,W,3]
+  const float* masks;    // [N,H,W,1]
+  float* origins;        // [R,3]
+  float* directions;     // [R,3]
+  int32_t* camera_indices;  // [R]
+  int64_t* indices;      // [R,3] (image, row, col) or NULL
+  float* image;          // [R,3]
+  float* fruit_mask;     // [R,1]
+};
+struct KSpacedBins {
+  int R, S, mode;        // mode 0 = uniform, 1 = linear-in-disparity piecewise
+  const float* base_bins;  // [S+1] linspace(0,1,S+1) made by the caller
+  const float* t_rand;   // NULL | [R] (t_stride 1) | [R,S+1]
+  int t_stride;
+  const float* nears;    // [R]
+  const float* fars;     // [R]
+  float* bins;           // [R,S+1]
+  float* starts;         // [R,S]
+  float* ends;           // [R,S]
+};
+struct KLosses {
+  int R;
+  float semantic_weight;
+  const float* rgb;        // [R,3]
+  const float* semantics;  // [R]
+  const float* image;      // [R,3]
+  const float* fruit_mask; // [R]
+  float* out;              // [4]: mse, weight*bce, psnr, -
+  float* d_rgb;            // [R,3] d mse / d rgb (may be NULL)
+  float* d_semantics;      // [R]   d (weight*bce) / d semantics (may be NULL)
+};
+struct KRayMetrics {
+  int R, S;
+  const float* weights;  // [R,S]
+  const float* sdist;    // [R,S+1] (distortion only)
+  const float* starts;   // [R,S]   (median depth only)
+  const float* ends;
+  float* distortion;     // scalar, pre-zeroed, or NULL
+  float* depth;          // [R] or NULL
+};
+int launch_pixel_batch(const KPixelBatch& A, cudaStream_t st);
+int launch_spaced_bins(const KSpacedBins& A, cudaStream_t st);
+int launch_render_losses(const KLosses& A, cudaStream_t st);
+int launch_ray_metrics(const KRayMetrics& A, cudaStream_t st);
+
 // ---- optimiser (fnr_optim.cu) ----
 constexpr int kMaxAdamTensors = 48;
 struct KAdamTensor {

@@ -108,6 +108,17 @@ class FruitDataManager(nn.Module):
         cams = ds.cameras
         N, H, W = len(ds), cams.height, cams.width
         dev = ds.images.device
+        if dev.type == "cuda":  # one launch (fnr_pixel_batch) after the draw, instead of ~25 indexing / elementwise kernels
+            from .. import ops
+
+            # the default generator (seeded per rank by the trainer) is the one torch can advance inside a captured graph
+            r = torch.rand((num_rays, 3), device=dev)
+            o, d, cam, idx, image, mask = ops.pixel_batch(r, cams.camera_to_worlds, ds.images, ds.fruit_masks, cams.fx, cams.fy, cams.cx, cams.cy)
+            pa = self.__dict__.setdefault("_pixel_area_cache", {})
+            if (num_rays, str(dev)) not in pa:
+                pa[(num_rays, str(dev))] = torch.full((num_rays, 1), 1.0 / (cams.fx * cams.fy), device=dev)
+            bundle = RayBundle(origins=o, directions=d, pixel_area=pa[(num_rays, str(dev))], camera_indices=cam[:, None])
+            return bundle, {"image": image, "fruit_mask": mask, "indices": idx}
         # CUDA: the default generator (seeded per rank by the trainer) -- the one torch can advance inside a captured graph
         r = torch.rand((num_rays, 3), device=dev, generator=None if dev.type == "cuda" else self._generator())
         extent = self.__dict__.setdefault("_extent_cache", {})

@@ -20,8 +20,8 @@ from . import ops
 
 def default_loss(outputs: Dict[str, Tensor], image: Tensor, fruit_mask: Tensor, semantic_loss_weight: float = 1.0) -> Tensor:
     """rgb MSE + semantic BCE-with-logits (get_loss_dict without the interlevel term)."""
-    return torch.nn.functional.mse_loss(image, outputs["rgb"]) + semantic_loss_weight * torch.nn.functional.binary_cross_entropy_with_logits(
-        outputs["semantics"][:, None], fruit_mask)
+    mse, bce, _ = ops.render_losses(outputs["rgb"], outputs["semantics"], image, fruit_mask, semantic_loss_weight)  # one launch
+    return mse + bce
 
 
 class GraphedTrainStep:

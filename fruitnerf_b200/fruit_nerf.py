@@ -80,6 +80,8 @@ def _sdist(ray_samples: RaySamples) -> Tensor:
 
 def _median_depth(weights: Tensor, ray_samples: RaySamples) -> Tensor:
     """nerfstudio DepthRenderer(method="median") for the proposal levels (visualisation outputs)."""
+    if weights.is_cuda:
+        return ops.median_depth(weights[..., 0], ray_samples.frustums.starts[..., 0], ray_samples.frustums.ends[..., 0])
     with torch.no_grad():
         steps = (ray_samples.frustums.starts + ray_samples.frustums.ends) / 2
         cum = torch.cumsum(weights[..., 0], dim=-1)
@@ -263,11 +265,7 @@ class FruitModel(nn.Module):
     def get_loss_dict(self, outputs, batch, metrics_dict=None):
         """fruit_nerf.py:359-372."""
         loss_dict = {}
-        image = batch["image"].to(self.device)
-        loss_dict["rgb_loss"] = self.rgb_loss(image, outputs["rgb"])
-        loss_dict["semantics_loss"] = self.config.semantic_loss_weight * self.binary_cross_entropy_loss(
-            outputs["semantics"], batch["fruit_mask"].to(self.device)
-        )
+        loss_dict["rgb_loss"], loss_dict["semantics_loss"], _ = self._fused_losses(outputs, batch)
         if self.training:
             loss_dict["interlevel_loss"] = ops.interlevel_loss(
                 [w[..., 0] for w in outputs["weights_list"]], [_sdist(rs) for rs in outputs["ray_samples_list"]], self.config.interlevel_loss_mult
@@ -276,16 +274,20 @@ class FruitModel(nn.Module):
 
     def get_metrics_dict(self, outputs, batch):
         """fruit_nerf.py:396-401: PSNR (data_range 1)."""
-        image = batch["image"].to(self.device)
-        mse = torch.mean((outputs["rgb"].detach() - image) ** 2)
-        metrics = {"psnr": -10.0 * torch.log10(mse)}
-        with torch.no_grad():  # nerfstudio distortion_loss on the final level: a logged metric only (fruit_nerf.py:400)
-            t, w = _sdist(outputs["ray_samples_list"][-1]), outputs["weights_list"][-1][..., 0]
-            ut = (t[..., 1:] + t[..., :-1]) / 2
-            inter = torch.sum(w * torch.sum(w[..., None, :] * torch.abs(ut[..., :, None] - ut[..., None, :]), dim=-1), dim=-1)
-            intra = torch.sum(w**2 * (t[..., 1:] - t[..., :-1]), dim=-1) / 3
-            metrics["distortion"] = torch.mean(inter + intra)
+        metrics = {"psnr": self._fused_losses(outputs, batch)[2]}
+        # nerfstudio distortion_loss on the final level: a logged metric only (fruit_nerf.py:400)
+        metrics["distortion"] = ops.distortion_metric(outputs["weights_list"][-1][..., 0], _sdist(outputs["ray_samples_list"][-1]))
         return metrics
+
+    def _fused_losses(self, outputs, batch):
+        """(MSELoss, semantic_loss_weight * BCEWithLogitsLoss, PSNR) from ONE launch, shared by get_metrics_dict and
+        get_loss_dict (the reference evaluates the MSE twice, fruit_nerf.py:361 and :398)."""
+        cached = outputs.get("_losses")
+        if cached is None:
+            cached = ops.render_losses(outputs["rgb"], outputs["semantics"], batch["image"].to(self.device), batch["fruit_mask"].to(self.device),
+                                       self.config.semantic_loss_weight)
+            outputs["_losses"] = cached
+        return cached
 
     def get_training_callbacks(self, training_callback_attributes=None) -> List[Dict]:
         """fruit_nerf.py:191-223: anneal the proposal weights before each iteration, count steps after."""

@@ -444,3 +444,92 @@ def interlevel_loss(weights_list: Sequence[Tensor], sdist_list: Sequence[Tensor]
     if total is None:
         total = torch.zeros((), dtype=torch.float32, device=w.device)
     return total
+
+
+# ======================================================================================================
+# Per-ray glue of a training iteration (fnr_glue.cu): one launch each instead of dozens of torch kernels
+# ======================================================================================================
+def pixel_batch(rand: Tensor, c2w: Tensor, images: Tensor, masks: Tensor, fx: float, fy: float, cx: float, cy: float):
+    """PixelSampler.sample + RayGenerator (fruit_datamanager.py:183-192).  Returns origins, directions [R,3], camera_indices
+    [R] int32, indices [R,3] int64, image [R,3], fruit_mask [R,1]."""
+    dev = _require_cuda(rand, c2w, images, masks)
+    R = rand.shape[0]
+    N, H, W = images.shape[0], images.shape[1], images.shape[2]
+    rand, c2w, images, masks = _f32c(rand), _f32c(c2w), _f32c(images), _f32c(masks)
+    f32 = dict(dtype=torch.float32, device=dev)
+    o, d, img, m = torch.empty((R, 3), **f32), torch.empty((R, 3), **f32), torch.empty((R, 3), **f32), torch.empty((R, 1), **f32)
+    cam = torch.empty((R,), dtype=torch.int32, device=dev)
+    idx = torch.empty((R, 3), dtype=torch.int64, device=dev)
+    L.check(L.load().fnr_pixel_batch(rand.data_ptr(), c2w.data_ptr(), images.data_ptr(), masks.data_ptr(), N, H, W, float(fx), float(fy),
+                                     float(cx), float(cy), R, o.data_ptr(), d.data_ptr(), cam.data_ptr(), idx.data_ptr(), img.data_ptr(),
+                                     m.data_ptr(), _stream(dev)))
+    return o, d, cam, idx, img, m
+
+
+def spaced_bins(base_bins: Tensor, t_rand: Optional[Tensor], nears: Tensor, fars: Tensor, num_samples: int, mode: int):
+    """SpacedSampler bins (spacing space) + euclidean starts / ends.  base_bins [S+1] (host-made linspace, already on the device)."""
+    dev = _require_cuda(base_bins, nears, fars)
+    R = nears.reshape(-1).shape[0]
+    nears, fars = _f32c(nears.reshape(-1)), _f32c(fars.reshape(-1))
+    stride = 0
+    if t_rand is not None:
+        t_rand = _f32c(t_rand)
+        stride = 1 if t_rand.numel() == R else num_samples + 1
+    f32 = dict(dtype=torch.float32, device=dev)
+    bins, starts, ends = torch.empty((R, num_samples + 1), **f32), torch.empty((R, num_samples), **f32), torch.empty((R, num_samples), **f32)
+    L.check(L.load().fnr_spaced_bins(_f32c(base_bins.reshape(-1)).data_ptr(), _ptr(t_rand), stride, nears.data_ptr(), fars.data_ptr(), R, num_samples,
+                                     mode, bins.data_ptr(), starts.data_ptr(), ends.data_ptr(), _stream(dev)))
+    return bins, starts, ends
+
+
+class _RenderLosses(torch.autograd.Function):
+    """(MSE(image, rgb), weight * BCEWithLogits(semantics, mask), PSNR) with the gradients produced by the same launch."""
+
+    @staticmethod
+    def forward(ctx, rgb, semantics, image, fruit_mask, weight: float):
+        dev = _require_cuda(rgb, semantics, image, fruit_mask)
+        R = rgb.shape[0]
+        rgb_c, sem_c = _f32c(rgb.detach()), _f32c(semantics.detach().reshape(-1))
+        out = torch.empty(4, dtype=torch.float32, device=dev)
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        d_rgb = torch.empty_like(rgb_c) if need else None
+        d_sem = torch.empty_like(sem_c) if need else None
+        L.check(L.load().fnr_render_losses(rgb_c.data_ptr(), sem_c.data_ptr(), _f32c(image).data_ptr(), _f32c(fruit_mask.reshape(-1)).data_ptr(), R,
+                                           float(weight), out.data_ptr(), _ptr(d_rgb), _ptr(d_sem), _stream(dev)))
+        ctx.saved = (d_rgb, d_sem, semantics.shape)
+        ctx.mark_non_differentiable(out)
+        return out[0], out[1], out
+    # out[0] / out[1] are views of `out`: returned as separate 0-d tensors that carry the graph
+
+    @staticmethod
+    def backward(ctx, g_mse, g_bce, _g_out):
+        d_rgb, d_sem, sem_shape = ctx.saved
+        gr = d_rgb * g_mse if (g_mse is not None and ctx.needs_input_grad[0]) else None
+        gs = (d_sem * g_bce).view(sem_shape) if (g_bce is not None and ctx.needs_input_grad[1]) else None
+        return gr, gs, None, None, None
+
+
+def render_losses(rgb: Tensor, semantics: Tensor, image: Tensor, fruit_mask: Tensor, semantic_weight: float = 1.0):
+    """Returns (rgb_loss, semantics_loss, psnr): nn.MSELoss, semantic_weight * nn.BCEWithLogitsLoss(mean), -10 log10(mse)."""
+    mse, bce, out = _RenderLosses.apply(rgb, semantics, image, fruit_mask, semantic_weight)
+    return mse, bce, out[2]
+
+
+def distortion_metric(weights: Tensor, sdist: Tensor) -> Tensor:
+    """nerfstudio distortion_loss([weights], [ray_samples]) for one level, mean over rays (no gradient: a logged metric)."""
+    dev = _require_cuda(weights, sdist)
+    R, S = weights.shape
+    out = torch.zeros((), dtype=torch.float32, device=dev)
+    L.check(L.load().fnr_ray_metrics(_f32c(weights.detach()).data_ptr(), _f32c(sdist.detach()).data_ptr(), None, None, R, S, out.data_ptr(), None,
+                                     _stream(dev)))
+    return out
+
+
+def median_depth(weights: Tensor, starts: Tensor, ends: Tensor) -> Tensor:
+    """DepthRenderer(method="median") of one level: [R,1]."""
+    dev = _require_cuda(weights, starts, ends)
+    R, S = weights.shape
+    depth = torch.empty((R, 1), dtype=torch.float32, device=dev)
+    L.check(L.load().fnr_ray_metrics(_f32c(weights.detach()).data_ptr(), None, _f32c(starts.detach()).data_ptr(), _f32c(ends.detach()).data_ptr(), R, S,
+                                     None, depth.data_ptr(), _stream(dev)))
+    return depth

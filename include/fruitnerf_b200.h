@@ -27,6 +27,11 @@
  *                        (fruit_nerf/fruit_nerf.py:149-206 construction, :320-321 call, :361-364
  *                        interlevel loss): HashMLPDensityField.get_density + get_weights,
  *                        PDFSampler.generate_ray_samples, nerfstudio losses.interlevel_loss
+ *   fnr_pixel_batch, fnr_spaced_bins, fnr_render_losses, fnr_ray_metrics
+ *                        the per-ray glue of a training iteration: pixel sampling + ray generation
+ *                        (fruit_nerf/data/fruit_datamanager.py:183-192), the initial spaced sampler
+ *                        (components/ray_samplers.py:54-104), losses and metrics (fruit_nerf.py:359-366, 396-401),
+ *                        proposal-level median depths (fruit_nerf.py:339-340)
  *   fnr_adam_step        torch.optim.Adam / RAdam over a param group (nerfstudio Optimizers; optimiser
  *                        settings fruit_nerf/fruit_nerf_config.py:47-56, 90-103, 140-153)
  */
@@ -245,6 +250,38 @@ typedef struct fnr_adam_tensor {
  * `hyper` is a DEVICE array of 8 floats {lr, beta1, beta2, eps, 1-beta1^t, 1-beta2^t, radam_rect (<0: not
  * rectified), grad_scale}: the schedule advances by rewriting it, so the launch can live in a CUDA graph. */
 int fnr_adam_step(const fnr_adam_tensor* tensors, int32_t count, int32_t kind, const float* hyper, void* stream);
+
+/* ---- per-ray glue of a training iteration (fnr_glue.cu) ---------------------------------------------------- */
+
+/* PixelSampler.sample + RayGenerator for a pinhole camera set held in device memory
+ * (fruit_nerf/data/fruit_datamanager.py:183-192): rand [R,3] uniform draws -> (image, row, col) = floor(rand*[N,H,W]);
+ * origins / directions [R,3] (pixel centres, normalised, OpenGL c2w [N,3,4]), camera_indices [R] int32,
+ * indices [R,3] int64 (may be NULL), image [R,3] and fruit_mask [R,1] gathered from images [N,H,W,3] / masks [N,H,W,1]. */
+int fnr_pixel_batch(const float* rand, const float* c2w, const float* images, const float* masks, int32_t num_images,
+                    int32_t height, int32_t width, float fx, float fy, float cx, float cy, int32_t num_rays, float* origins,
+                    float* directions, int32_t* camera_indices, int64_t* indices, float* image, float* fruit_mask,
+                    void* stream);
+
+#define FNR_SPACING_UNIFORM 0
+#define FNR_SPACING_LINDISP_PIECEWISE 1
+/* SpacedSampler.generate_ray_samples (components/ray_samplers.py:54-104; nerfstudio UniformLinDispPiecewiseSampler):
+ * base_bins [S+1] = linspace(0,1,S+1) made by the caller; t_rand NULL (eval) | [R] (t_stride 1, single jitter) |
+ * [R,S+1]; outputs spacing bins [R,S+1] and euclidean starts / ends [R,S]. */
+int fnr_spaced_bins(const float* base_bins, const float* t_rand, int32_t t_stride, const float* nears, const float* fars,
+                    int32_t num_rays, int32_t num_samples, int32_t mode, float* bins, float* starts, float* ends,
+                    void* stream);
+
+/* MSELoss(image, rgb), semantic_weight * BCEWithLogitsLoss(semantics, fruit_mask), PSNR (fruit_nerf.py:359-366,
+ * 396-399) in one launch: out[0..2] = {mse, weighted bce, psnr}; d_rgb [R,3] / d_semantics [R] receive the gradients
+ * of out[0] / out[1] (either may be NULL). */
+int fnr_render_losses(const float* rgb, const float* semantics, const float* image, const float* fruit_mask,
+                      int32_t num_rays, float semantic_weight, float* out, float* d_rgb, float* d_semantics,
+                      void* stream);
+
+/* nerfstudio distortion_loss of one level (mean over rays, ADDED to *distortion -- zero it first; fruit_nerf.py:400)
+ * and / or DepthRenderer(method="median") of a level (fruit_nerf.py:339-340).  Pass NULL for the part not wanted. */
+int fnr_ray_metrics(const float* weights, const float* sdist, const float* starts, const float* ends, int32_t num_rays,
+                    int32_t num_samples, float* distortion, float* median_depth, void* stream);
 
 int fnr_version(void);
 const char* fnr_last_error(void);
