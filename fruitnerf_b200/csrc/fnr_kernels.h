@@ -223,6 +223,9 @@ int launch_hash_indices(const KField& F, const KRays& Rr, int32_t* rows, float* 
 // fused tcgen05 forward (fnr_tc.cu).  Returns FNR_ERR_UNSUPPORTED when the shape is not covered.
 bool tc_supported(Family fam, const KField& F, const KRays& Rr);
 bool tc_export_supported(Family fam, const KExport& E);
+bool tc_big_supported(int S);
+int launch_tc_render_forward_big(const KField& F, const KParams& P, const KRays& Rr, const KFieldOut& O, const KComposite& Cm, cudaStream_t st);
+int launch_tc_export_big(const KField& F, const KParams& P, const KExport& E, cudaStream_t st);
 int launch_tc_export(Family fam, const KField& F, const KParams& P, const KExport& E, cudaStream_t st);
 int launch_tc_render_forward(Family fam, const KField& F, const KParams& P, const KRays& Rr, const KFieldOut& O,
                              const KComposite& Cm, cudaStream_t st);

@@ -258,8 +258,6 @@ def test_export_matches_oracle(native_lib, cuda_device, name, n, impl):
     all three sets are populated (the reference constants 3 / 70 / 0.9 are covered below)."""
     sd, spec = make_state(name, table_scale=2.0, weight_gain=2.5)
     field = make_field(name, sd, spec, cuda_device, contraction=False, test_mode="export").eval()
-    if impl == L.FNR_IMPL_TCGEN05 and name != "small":
-        pytest.skip("tcgen05 export kernel serves the fruit_nerf family")
     pts, plane = ns.surface_points(((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0)), n)
     o, dirs, nears, fars = ns.orthographic_rays(pts, plane, batch=10_000, count=1)
     bins = torch.linspace(0.0, 1.0, n + 1)
