@@ -217,6 +217,8 @@ int fnr_render_backward_scratch_bytes(const fnr_field_desc* desc, int32_t num_ra
     return FNR_ERR_INVALID_ARGUMENT;
   }
   *bytes = (size_t)num_rays * num_samples * 5 * sizeof(float) + 256;
+  // the big-family tensor-core backward stages every layer's X / dY for the cuBLAS weight-gradient GEMMs (fnr_tc_big_bwd.cu)
+  if (classify(desc) == kFamilyBig && desc->impl != FNR_IMPL_SIMT) *bytes += tc_big_backward_scratch_bytes((long long)num_rays * num_samples) + 256;
   return FNR_OK;
 }
 
@@ -265,10 +267,17 @@ int fnr_render_backward(const fnr_field_desc* desc, const fnr_field_params* para
                   point_grads,
                   desc->pass_semantic_gradients};
   if ((rc = launch_simt_composite_backward(Rr, B, st))) return rc;
-  KFieldBwd FB{point_grads, saved->stash_encoding, saved->sample_rgb};
+  const size_t pg_bytes = ((size_t)Rr.R * Rr.S * 5 * sizeof(float) + 255) & ~(size_t)255;
+  uint8_t* extra = reinterpret_cast<uint8_t*>(point_grads) + pg_bytes;
+  const size_t used = (size_t)(extra - reinterpret_cast<uint8_t*>(scratch));
+  KFieldBwd FB{point_grads, saved->stash_encoding, saved->sample_rgb, scratch_bytes > used ? extra : nullptr,
+               scratch_bytes > used ? scratch_bytes - used : 0};
   int impl = desc->impl;
-  if (impl == FNR_IMPL_AUTO) impl = tc_backward_supported(fam, F, Rr, FB) ? FNR_IMPL_TCGEN05 : FNR_IMPL_SIMT;
+  const bool big_tc = fam == kFamilyBig && FB.extra_bytes >= tc_big_backward_scratch_bytes((long long)Rr.R * Rr.S) + 256 &&
+                      tc_big_backward_supported(F, FB);
+  if (impl == FNR_IMPL_AUTO) impl = (big_tc || tc_backward_supported(fam, F, Rr, FB)) ? FNR_IMPL_TCGEN05 : FNR_IMPL_SIMT;
   if (impl == FNR_IMPL_TCGEN05) {
+    if (big_tc) return launch_tc_big_field_backward(F, P, G, Rr, FB, st);
     if (!tc_backward_supported(fam, F, Rr, FB)) {
       set_error("tcgen05 backward kernel does not support this configuration");
       return FNR_ERR_UNSUPPORTED;

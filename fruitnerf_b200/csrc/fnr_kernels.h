@@ -76,6 +76,8 @@ struct KFieldBwd {
   const float* point_grads;     // [N,5]
   const float* stash_encoding;  // [N,32] or NULL (recompute)
   const float* sample_rgb;      // [N,3] forward rgb (tcgen05 backward: sigmoid' without re-running colour2)
+  void* extra;                  // big-family tensor-core backward: scratch for the per-point X / dY matrices
+  size_t extra_bytes;
 };
 
 struct KExport {
@@ -224,6 +226,9 @@ int launch_hash_indices(const KField& F, const KRays& Rr, int32_t* rows, float* 
 bool tc_supported(Family fam, const KField& F, const KRays& Rr);
 bool tc_export_supported(Family fam, const KExport& E);
 bool tc_big_supported(int S);
+size_t tc_big_backward_scratch_bytes(long long num_points);
+bool tc_big_backward_supported(const KField& F, const KFieldBwd& B);
+int launch_tc_big_field_backward(const KField& F, const KParams& P, const KParams& G, const KRays& Rr, const KFieldBwd& B, cudaStream_t st);
 int launch_tc_render_forward_big(const KField& F, const KParams& P, const KRays& Rr, const KFieldOut& O, const KComposite& Cm, cudaStream_t st);
 int launch_tc_export_big(const KField& F, const KParams& P, const KExport& E, cudaStream_t st);
 int launch_tc_export(Family fam, const KField& F, const KParams& P, const KExport& E, cudaStream_t st);
