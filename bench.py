@@ -265,7 +265,8 @@ def run_ours(args):
     on_tc = args.variant == "small" and args.kernel != "simt"  # the families the tcgen05 kernels serve (fnr_api.cu dispatch)
     fwd_kernel = ("tc_render_forward_kernel" if on_tc else
                   "tc_render_forward_big_kernel" if args.kernel != "simt" else "simt_field_forward_kernel + simt_composite_kernel")
-    bwd_kernel = "tc_field_backward_kernel" if on_tc else "simt_field_backward_kernel"
+    bwd_kernel = ("tc_field_backward_kernel" if on_tc else
+                  "tc_big_backward_chain_kernel + cuBLAS dW GEMMs" if args.kernel != "simt" else "simt_field_backward_kernel")
     line = {
         "metric": "rays/sec (4096 rays x 192 samples) fused fwd+bwd",
         "value": world * R_RAYS * args.steps / (total_ms * 1e-3),

@@ -24,7 +24,17 @@ using namespace tcx;
 
 namespace {
 
-constexpr int kCtaThreads = 256;
+constexpr int kComputeThreads = 256;  // 8 warps: the tensor chain (thread pair (row, half) per point)
+constexpr int kScatterThreads = 128;  // 4 warps: hash-table gradient reds of the previous tile, overlapped with the chain
+                                      // (8 scatter warps measured slower: 3.32 vs 3.07 ms backward phase -- the reds contend)
+constexpr int kCtaThreads = kComputeThreads + kScatterThreads;
+constexpr int BAR_COMPUTE = 1, BAR_FULL = 2, BAR_EMPTY = 3;
+constexpr int STAGE_STRIDE = 36;  // floats per point in the hand-off buffer: denc[32], pos xyz, live flag
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 constexpr int GEO = 30, ENC = 32, H = 64, APP = 32, SHD = 16, SW = 128, SOUT = 64, CIN = SHD + GEO + APP;
 constexpr int K_BASE0 = 32, N_BASE0 = 64;
 constexpr int K_BASE1 = 64, N_BASE1 = 32;
@@ -44,18 +54,23 @@ constexpr int OFF_W_COL2 = OFF_W_COL1 + 2 * wbytes(N_COL1, K_COL1);
 constexpr int OFF_F32 = OFF_W_COL2 + 2 * wbytes(N_COL2, K_COL2);
 // floats: biases base0[64] base1[32] sem0[128] sem1[128] col0[64] col1[64] | fold[128]
 constexpr int B_BASE0 = 0, B_BASE1 = 64, B_SEM0 = 96, B_SEM1 = 224, B_COL0 = 352, B_COL1 = 416, B_FOLD = 480, B_COUNT = 608;
-constexpr int kSmemBytes = OFF_F32 + B_COUNT * 4 + 1024;
+constexpr int OFF_STAGE = OFF_F32 + B_COUNT * 4;
+constexpr int kSmemBytes = OFF_STAGE + 128 * STAGE_STRIDE * 4 + 1024;
+static_assert(OFF_STAGE % 16 == 0, "alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared-memory budget");
 
 constexpr int R_A0 = 0, R_A1 = 128, R_D0 = 256, R_D1 = 384;
 
 // scratch matrices (fp32, row-major, one row per point); X widths include the constant-1 column (+ padding to 4 floats)
-constexpr int XW_E = 36, XW_H = 68, XW_G = 36, XW_Z = 132, XW_C = 84, XW_C1 = 68, XW_C2 = 68;
-constexpr int DW_H = 64, DW_OUT = 32, DW_Z = 128, DW_C = 64, DW_R = 4;
+// every width is a multiple of 8 floats so that each thread writes whole 32-byte sectors (st.global.v8.f32);
+// layouts: XE [enc 32 | 1 | 0..], XH [h 64 | 1 | ..], XG [h0-slot, geo 30, pad | 1 | ..] (the kernel's K order),
+// XZ [z 128 | 1 | ..], XC [sh 16 | app 32 | h0-slot, geo 30, pad | 1 | ..] (kernel K order; big_unpack_kernel permutes)
+constexpr int XW_E = 40, XW_H = 72, XW_G = 40, XW_Z = 136, XW_C = 88, XW_C1 = 72, XW_C2 = 72;
+constexpr int DW_H = 64, DW_OUT = 32, DW_Z = 128, DW_C = 64, DW_R = 8;
 constexpr int kFloatsPerPoint = XW_E + XW_H + XW_G + 2 * XW_Z + XW_C + XW_C1 + XW_C2 + DW_H + DW_OUT + 2 * DW_Z + 2 * DW_C + DW_R;
 // GEMM outputs C_l [N_l x XW_l]
 constexpr int CO_B0 = 0, CO_B1 = CO_B0 + 64 * XW_E, CO_S0 = CO_B1 + 32 * XW_H, CO_S1 = CO_S0 + 128 * XW_G, CO_F = CO_S1 + 128 * XW_Z,
-              CO_C0 = CO_F + XW_Z, CO_C1 = CO_C0 + 64 * XW_C, CO_C2 = CO_C1 + 64 * XW_C1, CO_END = CO_C2 + 4 * XW_C2;
+              CO_C0 = CO_F + 4 * XW_Z, CO_C1 = CO_C0 + 64 * XW_C, CO_C2 = CO_C1 + 64 * XW_C1, CO_END = CO_C2 + 4 * XW_C2;
 
 struct Bufs {
   float *xe, *xh, *xg, *xz1, *xz2, *xc, *xc1, *xc2;
@@ -72,6 +87,7 @@ struct ChainArgs {
   const float* stash;
   const float* sample_rgb;
   Bufs B;
+  int debug_flags;  // FNR_DEBUG_BWD (timing experiments only): bit 0 skip the table scatter, bit 2 skip the X / dY stores
 };
 
 template <int K>
@@ -83,11 +99,17 @@ __device__ __forceinline__ void st_a16(uint32_t ab, int k0, const float (&v)[16]
   tmem_st8(ab + K / 2 + (k0 >> 1), l);
 }
 
-__device__ __forceinline__ void store16(float* dst, const float (&v)[16]) {
-  float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) d4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+// 256-bit stores (STG.E.ENL2.256): one whole 32-byte sector per lane and instruction; dst must be 32-byte aligned
+__device__ __forceinline__ void store8(float* dst, float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(a0), "f"(a1), "f"(a2), "f"(a3), "f"(a4), "f"(a5), "f"(a6),
+               "f"(a7)
+               : "memory");
 }
+__device__ __forceinline__ void store16(float* dst, const float (&v)[16]) {
+  store8(dst, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+  store8(dst + 8, v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
+}
+__device__ __forceinline__ void store_one_col(float* dst) { store8(dst, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f); }
 
 // forward GEMM: A (TMEM, depth K) x W[N,K]^T
 template <int K, int N>
@@ -126,13 +148,15 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
   __shared__ uint32_t s_tmem_base;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool is_compute = tid < kComputeThreads;
   const int half = (warp >> 2) & 1;
-  const int row = (warp & 3) * 32 + lane;
+  const int row = (warp & 3) * 32 + lane;  // compute: TMEM lane / point of the tile; scatter warps 8..11: the point they scatter
   const KParams& P = a.P;
   const KParams& G = a.G;
   const KField& F = a.F;
   const Bufs& B = a.B;
   float* sf = reinterpret_cast<float*>(smem + OFF_F32);
+  float* stage = reinterpret_cast<float*>(smem + OFF_STAGE);
 
   if (warp == 0) tmem_alloc(&s_tmem_base, 512);
   if (tid == 0) {
@@ -185,11 +209,11 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
   const uint32_t hmask = (1u << F.log2T) - 1u;
   float2* const gtab = reinterpret_cast<float2*>(G.hash_table);
 
-#define FNR_ISSUE(...)          \
-  tmem_st_wait();               \
-  fence_before_sync();          \
-  __syncthreads();              \
-  if (warp == 0) {              \
+#define FNR_ISSUE(...)                          \
+  tmem_st_wait();                               \
+  fence_before_sync();                          \
+  named_bar_sync(BAR_COMPUTE, kComputeThreads); \
+  if (warp == 0) {                              \
     if (elect_one_sync()) {     \
       fence_after_sync();       \
       __VA_ARGS__;              \
@@ -202,23 +226,70 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
   phase ^= 1;               \
   fence_after_sync();
 
+  if (!is_compute) {
+    // ================= scatter warps: hash-table gradient reds, decoupled from the tensor chain =================
+    reg_dec<72>();
+    const bool do_scatter = !(a.debug_flags & 1);
+    named_bar_arrive(BAR_EMPTY, kCtaThreads);
+#pragma unroll 1
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      named_bar_sync(BAR_FULL, kCtaThreads);
+      float g[32];
+      const float4* src = reinterpret_cast<const float4*>(stage + row * STAGE_STRIDE);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 v = src[q];
+        g[4 * q] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w;
+      }
+      const float4 pv = src[8];
+      if (tile + gridDim.x < tiles) named_bar_arrive(BAR_EMPTY, kCtaThreads);  // the hand-off buffer may be overwritten
+      const Vec3 pos = {pv.x, pv.y, pv.z};
+      if (pv.w != 0.f && do_scatter) {
+#pragma unroll
+        for (int l = 0; l < 16; ++l) {
+          const float g0 = g[2 * l], g1 = g[2 * l + 1];
+          if (g0 != 0.f || g1 != 0.f) {
+            const LevelCell c = level_cell(pos, F.scalings[l]);
+            const uint32_t base = (uint32_t)l << F.log2T;
+            const bool pair = ((c.hx[0] & 1u) == 0u) && (c.hx[1] == c.hx[0] + 1u);  // x-neighbours: one 16-byte red
+            constexpr int kf[4] = {6, 7, 2, 3}, kc[4] = {5, 4, 1, 0};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float wf = corner_weight(c, kf[q]), wc = corner_weight(c, kc[q]);
+              const uint32_t rf = corner_row(c, kf[q], hmask, base);
+              if (pair) {
+                const uint32_t r0 = rf & ~1u;
+                const bool f_first = (rf & 1u) == 0u;
+                const float4 v = f_first ? make_float4(wf * g0, wf * g1, wc * g0, wc * g1) : make_float4(wc * g0, wc * g1, wf * g0, wf * g1);
+                atomicAdd(reinterpret_cast<float4*>(gtab + r0), v);
+              } else {
+                if (wf != 0.f) atomicAdd(gtab + rf, make_float2(wf * g0, wf * g1));
+                if (wc != 0.f) atomicAdd(gtab + corner_row(c, kc[q], hmask, base), make_float2(wc * g0, wc * g1));
+              }
+            }
+          }
+        }
+      }
+    }
+  } else {
+  // ================= compute warps =================
+  reg_inc<216>();
 #pragma unroll 1
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const long long p = tile * 128 + row;
-    const bool valid = p < N;
-    const long long pc = valid ? p : N - 1;
+    const bool in_range = p < N;
+    const bool valid = in_range && !(a.debug_flags & 4);  // `valid` guards the scratch stores
+    const long long pc = in_range ? p : N - 1;
     const int ray = (int)(pc / S);
     const float* o = a.Rr.origins + 3 * (size_t)ray;
     const float* d = a.Rr.directions + 3 * (size_t)ray;
     bool sel;
     const Vec3 pos = field_position(o, d, __ldg(a.Rr.starts + pc), __ldg(a.Rr.ends + pc), F.position_mode, F.aabb, sel);
-    const float vm = valid ? 1.f : 0.f;
+    const float vm = in_range ? 1.f : 0.f;
     const float* pg = a.point_grads + 5 * (size_t)pc;
     const float d_sigma = __ldg(pg) * vm;
     const float d_logit = __ldg(pg + 4) * vm;
     const int cam = (F.appearance_mode == FNR_APP_PER_CAMERA) ? __ldg(a.Rr.camera_indices + ray) : 0;
-    const float one_col[4] = {1.f, 0.f, 0.f, 0.f};
-    const float4 ones4 = make_float4(one_col[0], one_col[1], one_col[2], one_col[3]);
 
     // ---- R1: encoding (stash) -> A0 ; X_enc ----
     {
@@ -232,7 +303,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
       st_a16<K_BASE0>(tr + R_A0, 16 * half, enc);
       if (valid) {
         store16(B.xe + (size_t)p * XW_E + 16 * half, enc);
-        if (half == 1) *reinterpret_cast<float4*>(B.xe + (size_t)p * XW_E + 32) = ones4;
+        if (half == 1) store_one_col(B.xe + (size_t)p * XW_E + 32);
       }
     }
     FNR_ISSUE(issue_fwd<K_BASE0, N_BASE0>(tb + R_D0, tb + R_A0, wBase + OFF_W_BASE0))
@@ -254,7 +325,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
       st_a16<K_BASE1>(tr + R_A1, 32 * half + 16 * j, v);
       if (valid) store16(B.xh + (size_t)p * XW_H + 32 * half + 16 * j, v);
     }
-    if (valid && half == 1) *reinterpret_cast<float4*>(B.xh + (size_t)p * XW_H + 64) = ones4;
+    if (valid && half == 1) store_one_col(B.xh + (size_t)p * XW_H + 64);
     if (half == 0) {
       float sh[16];
       sh_degree4(__ldg(d), __ldg(d + 1), __ldg(d + 2), sh);
@@ -268,18 +339,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] = app ? __ldg(app + 16 * j + q) : 0.f;
         st_a16<K_COL0>(tr + R_A0, SHD + 16 * j, v);
-        if (valid) {  // torch order [sh | geo | app]: app starts at column 46 (8-byte aligned only)
-          float2* dst = reinterpret_cast<float2*>(B.xc + (size_t)p * XW_C + SHD + GEO + 16 * j);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) dst[q] = make_float2(v[2 * q], v[2 * q + 1]);
-        }
+        if (valid) store16(B.xc + (size_t)p * XW_C + SHD + 16 * j, v);
       }
-      if (valid) {  // constant-1 column at 78, zero padding to 84
-        float2* dst = reinterpret_cast<float2*>(B.xc + (size_t)p * XW_C + CIN);
-        dst[0] = make_float2(1.f, 0.f);
-        dst[1] = make_float2(0.f, 0.f);
-        dst[2] = make_float2(0.f, 0.f);
-      }
+      if (valid) store_one_col(B.xc + (size_t)p * XW_C + K_COL0);
     }
     FNR_ISSUE(issue_fwd<K_BASE1, N_BASE1>(tb + R_D1, tb + R_A1, wBase + OFF_W_BASE1))
 
@@ -297,25 +359,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
       st_a16<K_SEM0>(tr + R_A1 + 64, 16 * half, g);
       st_a16<K_COL0>(tr + R_A0, SHD + APP + 16 * half, g);
       if (valid) {
-        // geo index of g[q]: half 0 -> q - 1 (q >= 1), half 1 -> 15 + q (q <= 14)
-        float* xg = B.xg + (size_t)p * XW_G;
-        float* xc = B.xc + (size_t)p * XW_C + SHD;
-        if (half == 0) {
-#pragma unroll
-          for (int q = 1; q < 16; ++q) {
-            xg[q - 1] = g[q];
-            xc[q - 1] = g[q];
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 15; ++q) {
-            xg[15 + q] = g[q];
-            xc[15 + q] = g[q];
-          }
-          xg[30] = 1.f;
-#pragma unroll
-          for (int q = 31; q < XW_G; ++q) xg[q] = 0.f;
-        }
+        store16(B.xg + (size_t)p * XW_G + 16 * half, g);
+        store16(B.xc + (size_t)p * XW_C + SHD + APP + 16 * half, g);
+        if (half == 1) store_one_col(B.xg + (size_t)p * XW_G + 32);
       }
     }
     FNR_ISSUE(issue_fwd<K_SEM0, N_SEM0>(tb + R_D0, tb + R_A1 + 64, wBase + OFF_W_SEM0);
@@ -353,8 +399,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
       if (valid) store16(B.xc1 + (size_t)p * XW_C1 + 32 * half + 16 * j, v);
     }
     if (valid && half == 1) {
-      *reinterpret_cast<float4*>(B.xz1 + (size_t)p * XW_Z + 128) = ones4;
-      *reinterpret_cast<float4*>(B.xc1 + (size_t)p * XW_C1 + 64) = ones4;
+      store_one_col(B.xz1 + (size_t)p * XW_Z + 128);
+      store_one_col(B.xc1 + (size_t)p * XW_C1 + 64);
     }
     FNR_ISSUE(issue_fwd<K_SEM1, N_SEM1>(tb + R_D0, tb + R_A1, wBase + OFF_W_SEM1);
               issue_fwd<K_COL1, N_COL1>(tb + R_D1, tb + R_A0, wBase + OFF_W_COL1))
@@ -394,8 +440,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
       if (valid) store16(B.xc2 + (size_t)p * XW_C2 + 32 * half + 16 * j, v);
     }
     if (valid && half == 1) {
-      *reinterpret_cast<float4*>(B.xz2 + (size_t)p * XW_Z + 128) = ones4;
-      *reinterpret_cast<float4*>(B.xc2 + (size_t)p * XW_C2 + 64) = ones4;
+      store_one_col(B.xz2 + (size_t)p * XW_Z + 128);
+      store_one_col(B.xc2 + (size_t)p * XW_C2 + 64);
     }
     if (half == 0) {
       float dr[16];
@@ -407,7 +453,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
         dr[c] = __ldg(pg + 1 + c) * vm * rgb * (1.0f - rgb);  // sigmoid'
       }
       st_a16<16>(tr + R_A0, 0, dr);
-      if (valid) *reinterpret_cast<float4*>(B.dr + (size_t)p * DW_R) = make_float4(dr[0], dr[1], dr[2], 0.f);
+      if (valid) store8(B.dr + (size_t)p * DW_R, dr[0], dr[1], dr[2], 0.f, d_logit, 0.f, 0.f, 0.f);  // columns 4..7: dY of the folded tail
     }
     FNR_ISSUE(issue_dx<N_SEM1, K_SEM1>(tb + R_D0, tb + R_A1, wBase + OFF_W_SEM1);
               issue_dx<N_COL2, K_COL2>(tb + R_D1, tb + R_A0, wBase + OFF_W_COL2))
@@ -464,7 +510,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
         if (uniform) {  // transposed butterfly: lane L ends with the (half-)sum of value L >> 1
           float w[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) w[i] = valid ? __uint_as_float(ra[i]) : 0.f;
+          for (int i = 0; i < 16; ++i) w[i] = in_range ? __uint_as_float(ra[i]) : 0.f;
 #pragma unroll
           for (int off = 16, n = 8; off >= 2; off >>= 1, n >>= 1) {
             const bool hi = (lane & off) != 0;
@@ -479,7 +525,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
           }
           const float tot = w[0] + __shfl_xor_sync(kTcFullMask, w[0], 1);
           if ((lane & 1) == 0 && tot != 0.f) atomicAdd(G.app_embedding + (size_t)cam * APP + 16 * half + (lane >> 1), tot);
-        } else if (valid) {
+        } else if (in_range) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float v = __uint_as_float(ra[i]);
@@ -512,42 +558,23 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
     }
     FNR_ISSUE(issue_dx<N_BASE0, K_BASE0>(tb + R_D0, tb + R_A0, wBase + OFF_W_BASE0))
 
-    // ---- epi10: d enc -> hash-table gradient (this thread's 8 levels) ----
+    // ---- epi10: d enc -> hand-off to the scatter warps ----
     FNR_WAIT()
     {
       uint32_t r[16];
       tmem_ld16(tr + R_D0 + 16 * half, r);
       tmem_ld_wait();
-      if (valid) {
+      named_bar_sync(BAR_EMPTY, kCtaThreads);  // the scatter warps have copied the previous tile out
+      float4* dst = reinterpret_cast<float4*>(stage + row * STAGE_STRIDE + 16 * half);
 #pragma unroll
-        for (int li = 0; li < 8; ++li) {
-          const int l = 8 * half + li;
-          const float g0 = __uint_as_float(r[2 * li]), g1 = __uint_as_float(r[2 * li + 1]);
-          if (g0 != 0.f || g1 != 0.f) {
-            const LevelCell c = level_cell(pos, F.scalings[l]);
-            const uint32_t base = (uint32_t)l << F.log2T;
-            const bool pair = ((c.hx[0] & 1u) == 0u) && (c.hx[1] == c.hx[0] + 1u);  // x-neighbours: one 16-byte red
-            constexpr int kf[4] = {6, 7, 2, 3}, kc[4] = {5, 4, 1, 0};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float wf = corner_weight(c, kf[q]), wc = corner_weight(c, kc[q]);
-              const uint32_t rf = corner_row(c, kf[q], hmask, base);
-              if (pair) {
-                const uint32_t r0 = rf & ~1u;
-                const bool f_first = (rf & 1u) == 0u;
-                const float4 v = f_first ? make_float4(wf * g0, wf * g1, wc * g0, wc * g1) : make_float4(wc * g0, wc * g1, wf * g0, wf * g1);
-                atomicAdd(reinterpret_cast<float4*>(gtab + r0), v);
-              } else {
-                if (wf != 0.f) atomicAdd(gtab + rf, make_float2(wf * g0, wf * g1));
-                if (wc != 0.f) atomicAdd(gtab + corner_row(c, kc[q], hmask, base), make_float2(wc * g0, wc * g1));
-              }
-            }
-          }
-        }
-      }
+      for (int q = 0; q < 4; ++q)
+        dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+      if (half == 0) reinterpret_cast<float4*>(stage + row * STAGE_STRIDE + 32)[0] = make_float4(pos.x, pos.y, pos.z, in_range ? 1.f : 0.f);
     }
+    named_bar_arrive(BAR_FULL, kCtaThreads);
     fence_before_sync();
   }
+  }  // compute warps
 #undef FNR_ISSUE
 #undef FNR_WAIT
 
@@ -575,8 +602,8 @@ __global__ void __launch_bounds__(256) big_unpack_kernel(const float* __restrict
   for (int i = t; i < 128 * XW_G; i += nt) {
     const int n = i / XW_G, k = i % XW_G;
     const float v = c[CO_S0 + i];
-    if (k < GEO) G.sem_w[0][n * GEO + k] += v;
-    else if (k == GEO) G.sem_b[0][n] += v;
+    if (k >= 1 && k <= GEO) G.sem_w[0][n * GEO + (k - 1)] += v;  // column 0 is the h0 slot
+    else if (k == 32) G.sem_b[0][n] += v;
   }
   for (int i = t; i < 128 * XW_Z; i += nt) {
     const int n = i / XW_Z, k = i % XW_Z;
@@ -601,9 +628,11 @@ __global__ void __launch_bounds__(256) big_unpack_kernel(const float* __restrict
   }
   for (int i = t; i < 64 * XW_C; i += nt) {
     const int n = i / XW_C, k = i % XW_C;
-    const float v = c[CO_C0 + i];
-    if (k < CIN) G.col_w[0][n * CIN + k] += v;
-    else if (k == CIN) G.col_b[0][n] += v;
+    const float v = c[CO_C0 + i];  // kernel K order [sh | app | h0-slot, geo, pad | 1] -> torch order [sh | geo | app]
+    if (k < SHD) G.col_w[0][n * CIN + k] += v;
+    else if (k < SHD + APP) G.col_w[0][n * CIN + SHD + GEO + (k - SHD)] += v;
+    else if (k >= SHD + APP + 1 && k <= SHD + APP + GEO) G.col_w[0][n * CIN + SHD + (k - SHD - APP - 1)] += v;
+    else if (k == K_COL0) G.col_b[0][n] += v;
   }
   for (int i = t; i < 64 * XW_C1; i += nt) {
     const int n = i / XW_C1, k = i % XW_C1;
@@ -695,6 +724,10 @@ int launch_tc_big_field_backward(const KField& F, const KParams& P, const KParam
     configured = true;
   }
   ChainArgs a;
+  {
+    const char* e = getenv("FNR_DEBUG_BWD");
+    a.debug_flags = e ? atoi(e) : 0;
+  }
   a.F = F;
   a.P = P;
   a.G = G;
@@ -727,7 +760,7 @@ int launch_tc_big_field_backward(const KField& F, const KParams& P, const KParam
   if ((rc = gemm_dw(cb, B.dout, DW_OUT, 32, B.xh, XW_H, N, B.cout + CO_B1))) return rc;
   if ((rc = gemm_dw(cb, B.dz1, DW_Z, 128, B.xg, XW_G, N, B.cout + CO_S0))) return rc;
   if ((rc = gemm_dw(cb, B.dz2, DW_Z, 128, B.xz1, XW_Z, N, B.cout + CO_S1))) return rc;
-  if ((rc = gemm_dw(cb, Bw.point_grads + 4, 5, 1, B.xz2, XW_Z, N, B.cout + CO_F))) return rc;  // dY = d logit (column 4 of point_grads)
+  if ((rc = gemm_dw(cb, B.dr + 4, DW_R, 4, B.xz2, XW_Z, N, B.cout + CO_F))) return rc;  // dY = [d logit, 0, 0, 0]: row 0 = v | s
   if ((rc = gemm_dw(cb, B.dc1, DW_C, 64, B.xc, XW_C, N, B.cout + CO_C0))) return rc;
   if ((rc = gemm_dw(cb, B.dc2, DW_C, 64, B.xc1, XW_C1, N, B.cout + CO_C1))) return rc;
   if ((rc = gemm_dw(cb, B.dr, DW_R, 4, B.xc2, XW_C2, N, B.cout + CO_C2))) return rc;
