@@ -29,6 +29,7 @@ constexpr int kScatterThreads = 128;  // 4 warps: hash-table gradient reds of th
                                       // (8 scatter warps measured slower: 3.32 vs 3.07 ms backward phase -- the reds contend)
 constexpr int kCtaThreads = kComputeThreads + kScatterThreads;
 constexpr int BAR_COMPUTE = 1, BAR_FULL = 2, BAR_EMPTY = 3;
+constexpr int kAggLevels = 4;    // coarse levels whose reds are run-length aggregated across the warp
 constexpr int STAGE_STRIDE = 36;  // floats per point in the hand-off buffer: denc[32], pos xyz, live flag
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 template <int N>
@@ -244,9 +245,59 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
       const float4 pv = src[8];
       if (tile + gridDim.x < tiles) named_bar_arrive(BAR_EMPTY, kCtaThreads);  // the hand-off buffer may be overwritten
       const Vec3 pos = {pv.x, pv.y, pv.z};
-      if (pv.w != 0.f && do_scatter) {
+      const bool live = pv.w != 0.f;
+      if (do_scatter) {
+        // Levels 0..kAggLevels-1 (as in fnr_tc_bwd.cu): the 32 lanes of a warp are consecutive samples of a ray and share grid
+        // cells; a run of lanes in the same cell is summed with a segmented suffix scan and only its head lane issues the reds.
+#pragma unroll 1
+        for (int l = 0; l < kAggLevels; ++l) {
+          const LevelCell c = level_cell(pos, F.scalings[l]);
+          const uint32_t key = live ? (c.hx[0] ^ c.hy[0] ^ c.hz[0]) : (0x80000000u | (uint32_t)lane);
+          const uint32_t prev = __shfl_up_sync(kTcFullMask, key, 1);
+          const bool head = lane == 0 || prev != key;
+          const uint32_t heads = __ballot_sync(kTcFullMask, head);
+          const uint32_t above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
+          const int run_end = above ? (__ffs(above) - 1) : 32;
+          bool same[5];
 #pragma unroll
-        for (int l = 0; l < 16; ++l) {
+          for (int q = 0; q < 5; ++q) same[q] = lane + (1 << q) < run_end;
+          float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+          for (int ll = 0; ll < kAggLevels; ++ll)
+            if (ll == l) {
+              g0 = live ? g[2 * ll] : 0.f;
+              g1 = live ? g[2 * ll + 1] : 0.f;
+            }
+          float v0[8], v1[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float w = corner_weight(c, k);
+            v0[k] = w * g0;
+            v1[k] = w * g1;
+          }
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            const int dd = 1 << q;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float t0 = __shfl_down_sync(kTcFullMask, v0[k], dd), t1 = __shfl_down_sync(kTcFullMask, v1[k], dd);
+              if (same[q]) {
+                v0[k] += t0;
+                v1[k] += t1;
+              }
+            }
+          }
+          if (head && live) {
+            const uint32_t base = (uint32_t)l << F.log2T;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (v0[k] != 0.f || v1[k] != 0.f) atomicAdd(gtab + corner_row(c, k, hmask, base), make_float2(v0[k], v1[k]));
+          }
+        }
+      }
+      if (live && do_scatter) {
+#pragma unroll
+        for (int l = kAggLevels; l < 16; ++l) {
           const float g0 = g[2 * l], g1 = g[2 * l + 1];
           if (g0 != 0.f || g1 != 0.f) {
             const LevelCell c = level_cell(pos, F.scalings[l]);
