@@ -178,6 +178,10 @@ int fnr_render_forward(const fnr_field_desc* desc, const fnr_field_params* param
     set_error("out is NULL");
     return FNR_ERR_INVALID_ARGUMENT;
   }
+  if (out->stash_encoding && (reinterpret_cast<uintptr_t>(out->stash_encoding) & 31u)) {
+    set_error("stash_encoding must be 32-byte aligned (written with 256-bit stores)");
+    return FNR_ERR_INVALID_ARGUMENT;
+  }
   const Family fam = classify(desc);
   const KField F = make_field(desc);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -280,9 +280,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
           enc[2 * li + 1] = r.y;
         }
         if (a.O.stash_encoding && valid) {
-          float4* st = reinterpret_cast<float4*>(a.O.stash_encoding + gp * ENC + 16 * half);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) st[i] = make_float4(enc[4 * i], enc[4 * i + 1], enc[4 * i + 2], enc[4 * i + 3]);
+          float* st = a.O.stash_encoding + gp * ENC + 16 * half;  // 64-byte aligned: two whole sectors per thread
+          st_global_v8(st, enc[0], enc[1], enc[2], enc[3], enc[4], enc[5], enc[6], enc[7]);
+          st_global_v8(st + 8, enc[8], enc[9], enc[10], enc[11], enc[12], enc[13], enc[14], enc[15]);
         }
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {

@@ -135,7 +135,7 @@ typedef struct fnr_render_out {
   float* sample_density;             /* [R,S]   field outputs per sample ... */
   float* sample_rgb;                 /* [R,S,3] */
   float* sample_semantics;           /* [R,S]   (logit) */
-  float* stash_encoding;             /* [R,S,L*F] encoded features kept for the backward, or NULL */
+  float* stash_encoding;             /* [R,S,L*F] encoded features kept for the backward (32-byte aligned), or NULL */
   int32_t clamp_rgb;                 /* 1: eval-mode RGBRenderer (nan_to_num + clamp to [0,1]) */
 } fnr_render_out;
 
