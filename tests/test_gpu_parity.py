@@ -88,6 +88,30 @@ def test_field_forward_matches_oracle(native_lib, cuda_device, name, mode, impl)
         assert_rel(out[FieldHeadNames.SEMANTICS], ref["semantics"], what="semantics")
 
 
+@pytest.mark.parametrize("impl", IMPLS, ids=IMPL_IDS)
+def test_huge_variant_forward_matches_oracle(native_lib, cuda_device, impl):
+    """fruit_nerf_huge: the big network on a max_res 8192 grid (fruit_nerf_config.py:113-153), 64 samples per ray."""
+    v = dict(syn.BIG, max_res=8192)
+    sd = syn.field_state(geo=v["geo"], sem_dims=v["sem_dims"], log2_hashmap_size=21, num_images=5, table_scale=0.5, weight_gain=1.5)
+    spec = fr.FieldSpec(max_res=8192, log2_hashmap_size=21, geo_feat_dim=30)
+    from fruitnerf_b200.fruit_field import FruitField, SceneContraction
+
+    field = FruitField(aabb=sd["aabb"], num_images=5, geo_feat_dim=30, max_res=8192, log2_hashmap_size=21, num_layers_semantic=3,
+                       hidden_dim_semantics=128, use_semantics=True, num_semantic_classes=1, test_mode=None,
+                       spatial_distortion=SceneContraction(order=float("inf")))
+    field.load_state_dict(sd, strict=False)
+    field = field.to(cuda_device).train()
+    o, d, s, e, cam = _rays(100, 64, salt=8, far=3.0, num_images=5)
+    with torch.no_grad():
+        out = _render_gpu(field, o, d, s, e, cam, impl)
+    f = _oracle_field(sd, spec, o, d, s, e, cam, True, "train")
+    ref = fr.render(f, s[..., None], e[..., None], training=True)
+    assert_rel(out["sample_density"], f["density"][..., 0], what="density")
+    assert_rel(out["rgb"], ref["rgb"], what="rgb")
+    assert_rel(out["semantics"], ref["semantics"][..., 0], what="semantics")
+    _check_depth_index(out["depth_index"], ref, ref["weights"])
+
+
 def test_missing_camera_indices_raises(native_lib, cuda_device):
     sd, spec = make_state("small")
     field = make_field("small", sd, spec, cuda_device).train()
@@ -189,7 +213,7 @@ def _safe_ray_weights(f, R):
 
 
 @pytest.mark.parametrize("impl", [L.FNR_IMPL_SIMT, L.FNR_IMPL_AUTO], ids=["simt", "auto"])
-@pytest.mark.parametrize("name,R,S", [("small", 128, 48), ("big", 128, 48), ("small", 111, 50)])
+@pytest.mark.parametrize("name,R,S", [("small", 128, 48), ("big", 128, 48), ("small", 111, 50), ("big", 77, 37)])
 def test_backward_matches_oracle_autograd(native_lib, cuda_device, name, R, S, impl):
     """auto = fused tcgen05 forward + tensor-core backward where the shape is covered (small family),
     simt kernels otherwise; 111 x 50 = 5550 points exercises a ragged last tile and warps that span rays."""
