@@ -33,16 +33,22 @@ class GraphedTrainStep:
         dev = next(field.parameters()).device
         self.device = dev
         R, S = num_rays, num_samples
-        f32 = dict(dtype=torch.float32, device=dev)
-        self.static = {
-            "origins": torch.zeros(R, 3, **f32),
-            "directions": torch.zeros(R, 3, **f32),
-            "starts": torch.zeros(R, S, **f32),
-            "ends": torch.ones(R, S, **f32),
-            "camera_indices": torch.zeros(R, dtype=torch.int32, device=dev),
-            "image": torch.zeros(R, 3, **f32),
-            "fruit_mask": torch.zeros(R, 1, **f32),
-        }
+        # every static input is a view of ONE device byte buffer, so a batch that arrives packed in one pinned host
+        # buffer (``pack_batch``) is a single host->device copy per step (``load_packed``)
+        spec = (("origins", (R, 3), torch.float32), ("directions", (R, 3), torch.float32), ("starts", (R, S), torch.float32),
+                ("ends", (R, S), torch.float32), ("camera_indices", (R,), torch.int32), ("image", (R, 3), torch.float32),
+                ("fruit_mask", (R, 1), torch.float32))
+        self._layout, off = {}, 0
+        for name, shape, dtype in spec:
+            n = 1
+            for v in shape:
+                n *= v
+            self._layout[name] = (off, n * 4, shape, dtype)
+            off += (n * 4 + 255) // 256 * 256
+        self._flat_bytes = off
+        self._flat = torch.zeros(off, dtype=torch.uint8, device=dev)
+        self.static = {name: self._flat[o:o + nb].view(dtype).view(shape) for name, (o, nb, shape, dtype) in self._layout.items()}
+        self.static["ends"].fill_(1.0)
         self.params = field.kernel_params()
         self.loss: Optional[Tensor] = None
         self.outputs: Optional[Dict[str, Tensor]] = None
@@ -50,6 +56,9 @@ class GraphedTrainStep:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.use_graph = use_graph
         self._captured = False
+        self._copy_stream = None
+        self._staging = None
+        self._copy_done = None
 
     # ---- inputs -----------------------------------------------------------------------------------
     def load_batch(self, origins, directions, starts, ends, camera_indices, image, fruit_mask, non_blocking: bool = True) -> int:
@@ -64,6 +73,38 @@ class GraphedTrainStep:
             dst.copy_(t.reshape(dst.shape), non_blocking=non_blocking)
             n += dst.numel() * dst.element_size()
         return n
+
+    def pack_batch(self, origins, directions, starts, ends, camera_indices, image, fruit_mask) -> Tensor:
+        """Pack one batch into a pinned host byte buffer with the layout of the static device buffer (what a data loader
+        worker would fill)."""
+        flat = torch.zeros(self._flat_bytes, dtype=torch.uint8).pin_memory()
+        src = dict(origins=origins, directions=directions, starts=starts, ends=ends, camera_indices=camera_indices, image=image,
+                   fruit_mask=fruit_mask)
+        for name, (o, nb, shape, dtype) in self._layout.items():
+            flat[o:o + nb].view(dtype).view(shape).copy_(src[name].to(dtype).reshape(shape))
+        return flat
+
+    def load_packed(self, flat_host: Tensor, non_blocking: bool = True) -> int:
+        """ONE host->device copy of a packed batch; returns the payload bytes (without alignment padding)."""
+        self._flat.copy_(flat_host, non_blocking=non_blocking)
+        return sum(nb for _, nb, _, _ in self._layout.values())
+
+    def prefetch_packed(self, flat_host: Tensor) -> int:
+        """Start the host->device copy of the NEXT packed batch on a side stream while the current step runs;
+        ``commit_prefetched`` swaps it in with one device-to-device copy."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._staging = torch.empty_like(self._flat)
+            self._copy_done = torch.cuda.Event()
+        self._copy_stream.wait_stream(torch.cuda.current_stream(self.device))  # the staging buffer was read by the last commit
+        with torch.cuda.stream(self._copy_stream):
+            self._staging.copy_(flat_host, non_blocking=True)
+            self._copy_done.record(self._copy_stream)
+        return sum(nb for _, nb, _, _ in self._layout.values())
+
+    def commit_prefetched(self) -> None:
+        torch.cuda.current_stream(self.device).wait_event(self._copy_done)
+        self._flat.copy_(self._staging, non_blocking=True)
 
     # ---- the step ---------------------------------------------------------------------------------
     def _eager(self) -> Tensor:
