@@ -1,6 +1,7 @@
 // extern "C" entry points of libfruitnerf_b200.so: argument validation, conversion of the plain-C
 // structs of include/fruitnerf_b200.h into kernel arguments, dispatch between the fused tcgen05
-// kernel and the fp32 simt kernels.  No host synchronisation, no allocation.
+// kernels and the fp32 simt kernels.  No host synchronisation, no allocation (the one exception: the cuBLAS handle the
+// big-family backward creates at its first call, fnr_tc_big_bwd.cu).
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>

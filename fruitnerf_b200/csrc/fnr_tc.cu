@@ -20,8 +20,8 @@
 //     The last semantic layer (no activation) is folded into the 1-logit head at weight-staging time.
 //   * Compositing: per-sample density / rgb / logit stay in shared memory; one warp per ray scans.
 //
-// Shapes: the fruit_nerf family (geo 15, semantic 15-64-64, colour 63-64-64-3).  Everything else is
-// served by the simt kernels (tc_supported() == false).
+// Shapes: the fruit_nerf family (geo 15, semantic 15-64-64, colour 63-64-64-3).  The fruit_nerf_big family is dispatched to
+// fnr_tc_big.cu (activations in tensor memory); everything else is served by the simt kernels (tc_supported() == false).
 #include <cstdio>
 #include <cstdlib>
 #include "fnr_common.cuh"

@@ -4,7 +4,8 @@
  * One shared library (libfruitnerf_b200.so, sm_100a) behind the reference's Nerfstudio plugin
  * surface.  Plain C: no C++ or torch types cross this boundary.  Every buffer is a raw DEVICE
  * pointer allocated and owned by the caller (PyTorch on the Python side); the library keeps no
- * global state besides a thread-local error string.  All kernels are enqueued on the
+ * global state besides a thread-local error string and, once the fruit_nerf_big backward has run, a cuBLAS
+ * handle (resolved with dlopen; used for that family's weight-gradient GEMMs only).  All kernels are enqueued on the
  * `cudaStream_t` passed as `void* stream` and never synchronise the host.
  *
  * Return value of every entry point: 0 = OK, negative = error (see FNR_ERR_*); the message is
