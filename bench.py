@@ -325,7 +325,33 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args.variant, sample_rays=args.cpu_rays, repeats=1)
+    if world == 1 and not args.no_train:
+        line["train_iteration"] = train_iteration_rate(args.variant, dev)
     print(json.dumps(line))
+
+
+def train_iteration_rate(variant: str, dev, iterations: int = 300):
+    """Supplementary number (BASELINE.json configs[1]/[2]): a WHOLE training iteration of the method on the synthetic
+    apple scene -- pixel batch, proposal stage, field forward / backward, losses, Adam -- replayed as CUDA graphs by
+    fruitnerf_b200.trainer.Trainer.  Never allowed to break the headline line: any failure is reported as a string."""
+    try:
+        from fruitnerf_b200.scripts.train import synthetic_spec
+        from fruitnerf_b200.trainer import Trainer
+
+        method = "fruit_nerf" if variant == "small" else "fruit_nerf_big"
+        trainer = Trainer(synthetic_spec(method, schedule_steps=3000), device=dev, use_cuda_graph=True)
+        trainer.train(40)  # warm-up: eager iterations + capture of both schedule branches
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        trainer.train(iterations)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        rays = trainer.spec.pipeline.datamanager.train_num_rays_per_batch
+        return {"value": rays * iterations / dt, "unit": "rays/s", "ms_per_iteration": 1e3 * dt / iterations, "rays_per_iteration": rays,
+                "iterations": iterations, "method": method,
+                "what": "data + proposal sampling + field fwd/bwd + losses + optimiser, synthetic apple scene, CUDA-graph replay"}
+    except Exception as ex:  # noqa: BLE001
+        return {"error": f"{type(ex).__name__}: {ex}"[:300]}
 
 
 # per-launch DRAM traffic measured by ncu (profiles/r1_ncu_summary.md): tc_render_forward_kernel 57.9 MB read + 87.2 MB
@@ -409,6 +435,7 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--cpu-rays", type=int, default=2048)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the supplementary whole-training-iteration measurement")
     ap.add_argument("--no-graph", action="store_true", help="diagnostic: eager step instead of the CUDA-graph step")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic: skip the L2 flush between timed steps")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample nvidia-smi during the timed region")
