@@ -175,13 +175,14 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local) if (rank == 0 and not args.no_clocks) else None
+    if sampler:
+        sampler.start()  # before the barrier: host work on rank 0 between the barrier and the first timed step would show up
+                         # as a long first step on the other ranks (they wait in the all-reduce)
     if world > 1:
         import torch.distributed as dist
 
         dist.barrier()
     torch.cuda.synchronize()
-    if sampler:
-        sampler.start()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     for i in range(args.steps):
         if not args.no_flush:
@@ -196,6 +197,8 @@ def run_ours(args):
         dist.barrier()
     clocks = sampler.stop() if sampler else None
     step_ms = [ev[0].elapsed_time(ev[1]) for ev in evs]
+    if os.environ.get("FNR_BENCH_DEBUG"):
+        print(f"rank {rank} step_ms " + " ".join(f"{v:.3f}" for v in step_ms), file=sys.stderr)
     total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
     if world > 1:
         import torch.distributed as dist
