@@ -178,12 +178,12 @@ def run_ours(args):
     if sampler:
         sampler.start()  # before the barrier: host work on rank 0 between the barrier and the first timed step would show up
                          # as a long first step on the other ranks (they wait in the all-reduce)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     if world > 1:
         import torch.distributed as dist
 
         dist.barrier()
     torch.cuda.synchronize()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     for i in range(args.steps):
         if not args.no_flush:
             flush.fill_(float(i))  # evict the table / weights from L2 between timed steps
