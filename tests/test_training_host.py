@@ -143,3 +143,32 @@ def test_clustering_counts_blobs_and_merges_fragments():
     assert count_fruits(np.zeros((0, 3)), 0.1, 5, 0.1)["count"] == 0
     ds = voxel_down_sample(np.array([[0.0, 0, 0], [0.01, 0, 0], [1.0, 1, 1]]), 0.1)
     assert ds.shape == (2, 3)
+
+
+def test_synthetic_spec_keeps_reference_hyperparameters_and_optional_short_schedule():
+    from fruitnerf_b200.fruit_nerf_config import METHODS
+    from fruitnerf_b200.scripts.train import synthetic_spec
+
+    stock = synthetic_spec("fruit_nerf")
+    assert stock.optimizers["fields"]["scheduler"] == METHODS["fruit_nerf"].optimizers["fields"]["scheduler"]  # 1e-4 after 200 k steps
+    assert stock.pipeline.datamanager.synthetic_scene["num_fruits"] == 12
+    short = synthetic_spec("fruit_nerf_big", schedule_steps=1234)
+    for group in ("fields", "proposal_networks"):
+        assert short.optimizers[group]["scheduler"] == {"type": "ExponentialDecay", "lr_final": 1e-4, "max_steps": 1234}
+        assert short.optimizers[group]["optimizer"]["type"] == "RAdam"  # the optimiser itself is the method's
+    assert METHODS["fruit_nerf_big"].optimizers["proposal_networks"]["scheduler"] is None  # the shared config is not mutated
+
+
+def test_staged_device_buffer_on_cpu_and_export_slabs():
+    from fruitnerf_b200.export.exporter_utils import export_slab
+    from fruitnerf_b200.optim import StagedDeviceBuffer
+
+    buf = StagedDeviceBuffer(3, torch.device("cpu"), slots=2)
+    for k in range(5):  # more uploads than slots: the ring wraps
+        buf.upload([k, 2 * k, 3 * k])
+        assert buf.device_buffer.tolist() == [k, 2 * k, 3 * k]
+    # slabs: disjoint cover, empty slabs when there are more ranks than rays
+    for n, world in ((1000, 8), (5, 8), (0, 2), (262144, 3)):
+        slabs = [export_slab(n, world, r) for r in range(world)]
+        assert slabs[0][0] == 0 and slabs[-1][1] == n
+        assert all(lo <= hi for lo, hi in slabs) and all(slabs[i][1] == slabs[i + 1][0] for i in range(world - 1))
