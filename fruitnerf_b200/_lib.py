@@ -8,6 +8,7 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+ABI_VERSION = 2  # FNR_ABI_VERSION of include/fruitnerf_b200.h
 FNR_MAX_LEVELS = 32
 FNR_MAX_LAYERS = 4
 
@@ -118,6 +119,7 @@ class ExportParams(C.Structure):
         ("density_min", C.c_float),
         ("label_sigmoid_threshold", C.c_float),
         ("capacity", C.c_int32),
+        ("bins_ray_stride", C.c_int32),
     ]
 
 
@@ -239,7 +241,7 @@ def load() -> C.CDLL:
     lib.fnr_render_losses.argtypes = [vp, vp, vp, vp, i32, f32, vp, vp, vp, vp]
     lib.fnr_ray_metrics.restype = C.c_int
     lib.fnr_ray_metrics.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp]
-    if lib.fnr_version() != 1:
+    if lib.fnr_version() != ABI_VERSION:
         raise FruitNerfNativeError(f"ABI version mismatch: library reports {lib.fnr_version()}")
     _lib = lib
     return lib

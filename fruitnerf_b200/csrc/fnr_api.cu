@@ -321,6 +321,11 @@ int fnr_export_forward(const fnr_field_desc* desc, const fnr_field_params* param
   E.normal[1] = normal[1];
   E.normal[2] = normal[2];
   E.bins = bins;
+  if (xp->bins_ray_stride != 0 && xp->bins_ray_stride != num_samples + 1) {
+    set_error("bins_ray_stride must be 0 (shared bins) or num_samples + 1 (per-ray bins), got %d", xp->bins_ray_stride);
+    return FNR_ERR_INVALID_ARGUMENT;
+  }
+  E.bins_ray_stride = xp->bins_ray_stride;
   E.near_plane = near_plane;
   E.far_plane = far_plane;
   E.logit_min = xp->semantic_logit_min;

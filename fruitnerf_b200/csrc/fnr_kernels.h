@@ -84,7 +84,8 @@ struct KExport {
   int B, S;
   const float* origins;  // [B,3]
   float normal[3];
-  const float* bins;  // [S+1] spacing bins in [0,1]
+  const float* bins;  // [S+1] spacing bins in [0,1], or [B,S+1] with bins_ray_stride = S+1 (per-ray jitter)
+  int bins_ray_stride;
   float near_plane, far_plane;
   float logit_min, density_min, label_thr;
   int capacity;
@@ -231,6 +232,10 @@ bool tc_big_backward_supported(const KField& F, const KFieldBwd& B);
 int launch_tc_big_field_backward(const KField& F, const KParams& P, const KParams& G, const KRays& Rr, const KFieldBwd& B, cudaStream_t st);
 int launch_tc_render_forward_big(const KField& F, const KParams& P, const KRays& Rr, const KFieldOut& O, const KComposite& Cm, cudaStream_t st);
 int launch_tc_export_big(const KField& F, const KParams& P, const KExport& E, cudaStream_t st);
+// warp-specialised small-family forward / export (fnr_tc_ws.cu)
+bool tc_ws_supported(int S);
+int launch_tc_render_forward_ws(const KField& F, const KParams& P, const KRays& Rr, const KFieldOut& O, const KComposite& Cm, cudaStream_t st);
+int launch_tc_export_ws(const KField& F, const KParams& P, const KExport& E, cudaStream_t st);
 int launch_tc_export(Family fam, const KField& F, const KParams& P, const KExport& E, cudaStream_t st);
 int launch_tc_render_forward(Family fam, const KField& F, const KParams& P, const KRays& Rr, const KFieldOut& O,
                              const KComposite& Cm, cudaStream_t st);

@@ -702,7 +702,8 @@ __global__ void __launch_bounds__(kThreads) simt_export_kernel(KField F, KParams
     const int r = (int)(pc / E.S), s = (int)(pc % E.S);
     // UniformSamplerWithNoise (eval): bins = linspace(0,1,S+1) (made on the host, as the
     // reference does: components/ray_samplers.py:75); t = bins*far + (1-bins)*near
-    const float b0 = __ldg(E.bins + s), b1 = __ldg(E.bins + s + 1);
+    const float* bins = E.bins + (size_t)r * E.bins_ray_stride;  // per-ray jittered bins when the stride is S+1
+    const float b0 = __ldg(bins + s), b1 = __ldg(bins + s + 1);
     const float t0 = __fadd_rn(__fmul_rn(b0, E.far_plane), __fmul_rn(__fsub_rn(1.0f, b0), E.near_plane));
     const float t1 = __fadd_rn(__fmul_rn(b1, E.far_plane), __fmul_rn(__fsub_rn(1.0f, b1), E.near_plane));
     const float* o = E.origins + 3 * (size_t)r;

@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_kernel(const
       const float* d = kExport ? a.E.normal : a.Rr.directions + 3 * (size_t)ray;
       float t0, t1;
       if constexpr (kExport) {
-        export_interval(a.E, lc % S, t0, t1);
+        export_interval(a.E, ray, lc % S, t0, t1);
       } else {
         t0 = __ldg(a.Rr.starts + gp);
         t1 = __ldg(a.Rr.ends + gp);
@@ -439,6 +439,13 @@ bool tc_export_supported(Family fam, const KExport& E) {
   return fam == kFamilySmall && E.S >= 1 && E.S <= kMaxGroupPoints;
 }
 
+// FNR_FWD_V1=1 selects the round-1 kernel of this file (gather and chain in the same warps) for A/B timing
+static bool use_v1_forward() {
+  static int v = -1;
+  if (v < 0) v = getenv("FNR_FWD_V1") != nullptr;
+  return v != 0;
+}
+
 template <bool kExport>
 static int configure_tc_forward() {
   static bool configured = false;
@@ -458,6 +465,7 @@ int launch_tc_render_forward(Family fam, const KField& F, const KParams& P, cons
   }
   if (Rr.R == 0) return FNR_OK;
   if (fam == kFamilyBig) return launch_tc_render_forward_big(F, P, Rr, O, Cm, st);
+  if (!use_v1_forward()) return launch_tc_render_forward_ws(F, P, Rr, O, Cm, st);
   if (int rc = configure_tc_forward<false>()) return rc;
   TcArgs a;
   memset(&a.E, 0, sizeof(a.E));
@@ -484,6 +492,7 @@ int launch_tc_export(Family fam, const KField& F, const KParams& P, const KExpor
   }
   if (E.B == 0) return FNR_OK;
   if (fam == kFamilyBig) return launch_tc_export_big(F, P, E, st);
+  if (!use_v1_forward()) return launch_tc_export_ws(F, P, E, st);
   if (int rc = configure_tc_forward<true>()) return rc;
   TcArgs a;
   memset(&a, 0, sizeof(a));

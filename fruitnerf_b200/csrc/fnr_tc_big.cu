@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_big_kernel(c
       const float* d = kExport ? a.E.normal : a.Rr.directions + 3 * (size_t)ray;
       float t0, t1;
       if constexpr (kExport) {
-        export_interval(a.E, lc % S, t0, t1);
+        export_interval(a.E, ray, lc % S, t0, t1);
       } else {
         t0 = __ldg(a.Rr.starts + gp);
         t1 = __ldg(a.Rr.ends + gp);

@@ -23,9 +23,11 @@ __device__ __forceinline__ int warp_claim_rows(int* counter, bool pred, int lane
   return basev;
 }
 
-// UniformSamplerWithNoise in eval mode: t = bins*far + (1-bins)*near (components/ray_samplers.py:89-94)
-__device__ __forceinline__ void export_interval(const KExport& E, int s, float& t0, float& t1) {
-  const float b0 = __ldg(E.bins + s), b1 = __ldg(E.bins + s + 1);
+// UniformSamplerWithNoise: t = bins*far + (1-bins)*near (components/ray_samplers.py:89-94); bins are shared by all rays
+// (eval mode) or per ray (stratified jitter of the training-mode module, ray_samplers.py:78-87)
+__device__ __forceinline__ void export_interval(const KExport& E, int ray, int s, float& t0, float& t1) {
+  const float* bins = E.bins + (size_t)ray * E.bins_ray_stride;
+  const float b0 = __ldg(bins + s), b1 = __ldg(bins + s + 1);
   t0 = __fadd_rn(__fmul_rn(b0, E.far_plane), __fmul_rn(__fsub_rn(1.0f, b0), E.near_plane));
   t1 = __fadd_rn(__fmul_rn(b1, E.far_plane), __fmul_rn(__fsub_rn(1.0f, b1), E.near_plane));
 }
@@ -43,7 +45,7 @@ __device__ __forceinline__ void group_export(const KExport& E, const KField& F, 
     const float* q = s_samples + 5 * ic;
     const size_t p = gbase + ic;
     float t0, t1;
-    export_interval(E, ic % S, t0, t1);
+    export_interval(E, ray0 + ic / S, ic % S, t0, t1);
     bool sel;
     Vec3 world;
     (void)field_position(E.origins + 3 * (size_t)(ray0 + ic / S), E.normal, t0, t1, FNR_POS_AABB, F.aabb, sel, &world);

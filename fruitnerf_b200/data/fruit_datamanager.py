@@ -10,7 +10,7 @@ images from disk (nerfstudio's dataparser / dataloader machinery) is host I/O ou
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Dict, Optional, Tuple, Type, Union
+from typing import Any, Dict, Optional, Tuple, Type, Union
 
 import torch
 from torch import nn
@@ -64,6 +64,7 @@ class FruitDataManagerConfig(InstantiateConfig):
     train_num_rays_per_batch: int = 4096
     eval_num_rays_per_batch: int = 4096
     synthetic_scene: Optional[Dict] = None  # kwargs of data.synthetic_scene.make_apple_scene (no data set on disk)
+    dataparser: Optional[Any] = None        # FruitNerfDataParserConfig: read transforms.json + images + fruit masks from disk
     seed: int = 0
 
 
@@ -87,6 +88,12 @@ class FruitDataManager(nn.Module):
             from .synthetic_scene import make_apple_scene
 
             self.train_dataset, self.eval_dataset = make_apple_scene(**config.synthetic_scene)
+        self.train_dataparser_outputs = None
+        if self.train_dataset is None and config.dataparser is not None:
+            # fruit_datamanager.py:137-147 (dataparser -> train / eval data sets), decoded once into memory
+            from .fruitnerf_dataparser import load_fruit_datasets
+
+            self.train_dataset, self.eval_dataset, self.train_dataparser_outputs = load_fruit_datasets(config.dataparser)
         if self.train_dataset is not None and hasattr(self.train_dataset, "to"):
             self.train_dataset = self.train_dataset.to(device)
             if self.eval_dataset is not None:

@@ -245,7 +245,15 @@ class FruitModel(nn.Module):
         ``buffers`` is given the kernel also performs sample_volume's threshold + compaction."""
         S = self.num_inference_samples
         dev = ray_bundle.origins.device
-        bins = torch.linspace(0.0, 1.0, S + 1).to(dev)  # host linspace, as components/ray_samplers.py:75
+        sampler = self.proposal_sampler
+        if isinstance(sampler, UniformSamplerWithNoise) and sampler.train_stratified and sampler.training:
+            # The reference exporter calls setup_inference() AFTER eval_setup() put the pipeline in eval mode, so its
+            # freshly built sampler module is still in training mode and jitters every sample inside its bin
+            # (components/ray_samplers.py:78-87, single_jitter=False): per-ray bins [B, S+1].  `sampler.eval()` (or
+            # ExportSemanticPointCloud(stratified_jitter=False)) selects the deterministic regular grid instead.
+            bins = sampler.spacing_bins(ray_bundle.origins.shape[0], S, dev).contiguous()
+        else:
+            bins = torch.linspace(0.0, 1.0, S + 1).to(dev)  # host linspace, as components/ray_samplers.py:75
         normal = [float(v) for v in ray_bundle.directions[0].tolist()]
         near = float(ray_bundle.nears[0]) if ray_bundle.nears is not None else self.near_plane
         far = float(ray_bundle.fars[0]) if ray_bundle.fars is not None else self.far_plane

@@ -272,11 +272,17 @@ def export_batch(shape: FieldShape, params: Sequence[Tensor], origins: Tensor, n
     lib = L.load()
     origins = _f32c(origins)
     bins = _f32c(bins)
-    B, S = origins.shape[0], bins.numel() - 1
+    B = origins.shape[0]
+    if bins.dim() == 2 and bins.shape[0] != 1:  # per-ray bins [B, S+1]: the sampler's stratified jitter (training-mode module)
+        if bins.shape[0] != B:
+            raise ValueError(f"per-ray bins need one row per ray: {tuple(bins.shape)} for {B} rays")
+        S, stride = bins.shape[1] - 1, bins.shape[1]
+    else:
+        S, stride = bins.numel() - 1, 0
     params = [p.detach() for p in params]
     desc = shape.desc(L.FNR_POS_AABB, L.FNR_APP_MEAN, impl)
     pstruct = _params_struct(shape, params)
-    xp = L.ExportParams(float(thresholds[0]), float(thresholds[1]), float(thresholds[2]), buffers.capacity)
+    xp = L.ExportParams(float(thresholds[0]), float(thresholds[1]), float(thresholds[2]), buffers.capacity, stride)
     out = L.ExportOut()
     for k in range(3):
         out.rows[k] = buffers.rows[k].data_ptr()

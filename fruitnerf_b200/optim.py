@@ -74,7 +74,9 @@ class FusedAdam:
         self.kind = {"Adam": L.FNR_OPT_ADAM, "RAdam": L.FNR_OPT_RADAM}[kind]
         self.lr, self.eps, self.betas = lr, eps, betas
         self.scheduler = scheduler
-        self.step_count = 0
+        self.step_count = 0   # updates applied to this group (Adam bias correction)
+        self.sched_step = 0   # scheduler position = trainer iteration (nerfstudio steps every scheduler every iteration,
+                              # also on iterations where the group has no gradient and its optimiser is skipped)
         dev = self.params[0].device
         self.exp_avg = [torch.zeros_like(p) for p in self.params]
         self.exp_avg_sq = [torch.zeros_like(p) for p in self.params]
@@ -84,9 +86,11 @@ class FusedAdam:
         self._grad_ptrs = None
 
     # ---- hyper-parameters of the coming step (host side, tiny) -----------------------------------------
-    def _hyper_values(self, step: int, grad_scale: float) -> np.ndarray:
+    def _hyper_values(self, step: int, grad_scale: float, sched_step: Optional[int] = None) -> np.ndarray:
         b1, b2 = self.betas
-        lr = self.scheduler.lr(step - 1) * (self.lr / self.scheduler.lr_init) if self.scheduler else self.lr
+        if sched_step is None:
+            sched_step = self.sched_step
+        lr = self.scheduler.lr(sched_step) * (self.lr / self.scheduler.lr_init) if self.scheduler else self.lr
         bc1, bc2 = 1.0 - b1 ** step, 1.0 - b2 ** step
         rect = -1.0
         if self.kind == L.FNR_OPT_RADAM:
@@ -96,10 +100,21 @@ class FusedAdam:
                 rect = math.sqrt((rho_t - 4) * (rho_t - 2) * rho_inf / ((rho_inf - 4) * (rho_inf - 2) * rho_t))
         return np.array([lr, b1, b2, self.eps, bc1, bc2, rect, grad_scale], dtype=np.float32)
 
-    def prepare(self, grad_scale: float = 1.0) -> None:
-        """Advance the step counter and upload the hyper-parameters (async, from pinned memory)."""
+    def prepare(self, grad_scale: float = 1.0, sched_step: Optional[int] = None) -> None:
+        """Advance the update counter and upload the hyper-parameters (async, from pinned memory).  ``sched_step`` is the
+        trainer iteration the learning rate is read at (the reference's ``scheduler_step_all`` advances every scheduler
+        every iteration); without it the schedule advances once per call, which is only right for a group that is
+        stepped on every iteration."""
         self.step_count += 1
-        self._hyper.upload(self._hyper_values(self.step_count, grad_scale))
+        if sched_step is not None:
+            self.sched_step = int(sched_step)
+        self._hyper.upload(self._hyper_values(self.step_count, grad_scale, self.sched_step))
+        self._last_sched_step = self.sched_step
+        self.sched_step += 1
+
+    def skip(self) -> None:
+        """An iteration on which this group has no gradients: torch skips the update, the scheduler still advances."""
+        self.sched_step += 1
 
     def _tensor_array(self, grads: Sequence[Tensor]):
         ptrs = tuple(g.data_ptr() for g in grads)
@@ -123,20 +138,22 @@ class FusedAdam:
         dev = self.params[0].device
         L.check(L.load().fnr_adam_step(arr, len(self.params), self.kind, self.hyper.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
 
-    def step(self, grads: Optional[Sequence[Tensor]] = None, grad_scale: float = 1.0) -> None:
-        self.prepare(grad_scale)
+    def step(self, grads: Optional[Sequence[Tensor]] = None, grad_scale: float = 1.0, sched_step: Optional[int] = None) -> None:
+        self.prepare(grad_scale, sched_step)
         self.launch(grads)
 
     @property
     def current_lr(self) -> float:
-        return float(self._hyper_values(max(self.step_count, 1), 1.0)[0])
+        """Learning rate of the most recent update (of the coming one before any update)."""
+        return float(self._hyper_values(max(self.step_count, 1), 1.0, getattr(self, "_last_sched_step", self.sched_step))[0])
 
     # ---- checkpointing (nerfstudio stores optimizer.state_dict() per group) --------------------------------
     def state_dict(self) -> Dict:
-        return {"step": self.step_count, "exp_avg": [t.clone() for t in self.exp_avg], "exp_avg_sq": [t.clone() for t in self.exp_avg_sq]}
+        return {"step": self.step_count, "sched_step": self.sched_step, "exp_avg": [t.clone() for t in self.exp_avg], "exp_avg_sq": [t.clone() for t in self.exp_avg_sq]}
 
     def load_state_dict(self, sd: Dict) -> None:
         self.step_count = int(sd["step"])
+        self.sched_step = int(sd.get("sched_step", sd["step"]))
         for dst, src in zip(self.exp_avg, sd["exp_avg"]):
             dst.copy_(src)
         for dst, src in zip(self.exp_avg_sq, sd["exp_avg_sq"]):

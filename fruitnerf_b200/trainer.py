@@ -85,24 +85,25 @@ class Trainer:
         loss = sum(loss_dict.values())
         loss.backward()
         if with_optimizer:
-            self._exchange_and_step({name: [p.grad for p in params] for name, params in self.param_groups.items()}, launch_only)
+            self._exchange_and_step({name: [p.grad for p in params] for name, params in self.param_groups.items()}, launch_only, step)
         # detached: nothing may keep the autograd graph (and its AccumulateGrad nodes, which remember their stream) alive
         # across iterations -- a later CUDA-graph capture runs on a different stream
         return loss.detach(), {k: v.detach() for k, v in loss_dict.items()}, {k: v.detach() for k, v in metrics_dict.items()}
 
-    def _exchange_and_step(self, grads_by_group: Dict[str, list], launch_only: bool) -> None:
+    def _exchange_and_step(self, grads_by_group: Dict[str, list], launch_only: bool, step: Optional[int] = None) -> None:
         for name, opt in self.optimizers.items():
             grads = grads_by_group[name]
             if any(g is None for g in grads):
                 # torch optimisers skip parameters without a gradient: the proposal networks on the iterations the
-                # sampler runs them under no_grad (update_sched, fruit_nerf.py:131-136)
+                # sampler runs them under no_grad (update_sched, fruit_nerf.py:131-136).  Their learning-rate schedule
+                # still follows the trainer step (nerfstudio's scheduler_step_all): the next update reads lr(step).
                 continue
             if self.world_size > 1:
                 self._exchange(grads)
             if launch_only:
                 opt.launch(grads)
             else:
-                opt.step(grads)
+                opt.step(grads, sched_step=step)
 
     def train_iteration(self, step: int):
         self._run_callbacks("BEFORE_TRAIN_ITERATION", step)
@@ -113,7 +114,7 @@ class Trainer:
             updated = sampler.wants_update() if sampler is not None else True
             for name, opt in self.optimizers.items():  # advance the schedules of the groups this iteration steps
                 if updated or name != "proposal_networks":
-                    opt.prepare()
+                    opt.prepare(sched_step=step)
             if sampler is not None:
                 sampler.force_updated = updated
             if self._eager_iterations < self.graph_warmup:
@@ -143,7 +144,7 @@ class Trainer:
                 graph, result, static_grads = self._graphs[updated]
                 graph.replay()
                 if static_grads is not None:
-                    self._exchange_and_step(static_grads, launch_only=True)
+                    self._exchange_and_step(static_grads, launch_only=True, step=step)
                 self.pipeline.datamanager.train_count += 1
                 if sampler is not None and updated:
                     sampler._steps_since_update = 0

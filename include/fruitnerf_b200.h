@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define FNR_ABI_VERSION 1
+#define FNR_ABI_VERSION 2
 #define FNR_MAX_LEVELS 32
 #define FNR_MAX_LAYERS 4
 #define FNR_MAX_WIDTH 128
@@ -168,6 +168,10 @@ typedef struct fnr_export_params {
   float density_min;                 /* 70.0  : mask_den  = density >= 70   */
   float label_sigmoid_threshold;     /* 0.9   : label = heaviside(sigmoid(logit) - 0.9) */
   int32_t capacity;                  /* rows available in each of the three output sets */
+  int32_t bins_ray_stride;           /* 0: one bins[S+1] array shared by every ray (deterministic grid); S+1: per-ray
+                                      * bins[B,S+1] -- the stratified jitter UniformSamplerWithNoise applies while its
+                                      * module is in training mode (components/ray_samplers.py:78-87), which is the state
+                                      * the reference exporter runs it in (a module created after eval_setup()) */
 } fnr_export_params;
 
 typedef struct fnr_export_out {
@@ -302,7 +306,8 @@ int fnr_render_backward_scratch_bytes(const fnr_field_desc* desc, int32_t num_ra
 /* Uniform-volume export of one ray batch: rays are `origins[b] + t * normal` (normal = 3 HOST
  * floats), sample s spans t in [bins[s], bins[s+1]] * far + (1 - bins) * near where `bins` is a
  * DEVICE array of S+1 spacing bins in [0,1] (the reference builds it with torch.linspace on the
- * host, components/ray_samplers.py:75; the caller does the same so the bits agree).  The field
+ * host, components/ray_samplers.py:75; the caller does the same so the bits agree), or of
+ * [num_rays, S+1] per-ray jittered bins when xp->bins_ray_stride = S+1.  The field
  * runs in FNR_POS_AABB / FNR_APP_MEAN mode.  `point_base` is the global index of this batch's
  * first point (for `keys`). */
 int fnr_export_forward(const fnr_field_desc* desc, const fnr_field_params* params, const float* origins,

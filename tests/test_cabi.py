@@ -23,7 +23,7 @@ def test_header_symbols_are_exported(native_lib):
     for name in declared:
         assert hasattr(native_lib, name), f"{name} declared in include/fruitnerf_b200.h but not exported"
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared
-    assert native_lib.fnr_version() == 1
+    assert native_lib.fnr_version() == 2
 
 
 def test_struct_sizes_match_header(native_lib):

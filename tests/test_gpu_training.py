@@ -39,7 +39,14 @@ def test_fused_adam_matches_torch_optim(native_lib, cuda_device, kind):
     sd = opt.state_dict()
     opt2 = FusedAdam([p.detach().clone() for p in params], lr=1e-2, eps=1e-15, kind=kind, scheduler=sched)
     opt2.load_state_dict(sd)
-    assert opt2.step_count == 12 and torch.equal(opt2.exp_avg[0], opt.exp_avg[0])
+    assert opt2.step_count == 12 and opt2.sched_step == 12 and torch.equal(opt2.exp_avg[0], opt.exp_avg[0])
+    # a group skipped on some iterations: the learning rate is read at the trainer step, the bias correction at the update count
+    opt3 = FusedAdam([p.detach().clone() for p in params], lr=1e-2, eps=1e-15, kind=kind, scheduler=sched)
+    opt3.prepare(sched_step=30)
+    assert opt3.step_count == 1 and opt3.current_lr == pytest.approx(sched.lr(30), rel=1e-6)
+    opt3.skip()
+    opt3.prepare()
+    assert opt3.step_count == 2 and opt3.current_lr == pytest.approx(sched.lr(32), rel=1e-6)
 
 
 def _tiny_spec(seed=0):
@@ -71,6 +78,13 @@ def test_training_reduces_loss_and_raises_psnr(trained):
     # both param groups were stepped (the proposal group only on the iterations its networks ran with grad)
     assert trainer.optimizers["fields"].step_count == 400
     assert 50 < trainer.optimizers["proposal_networks"].step_count <= 400
+    # schedules follow the TRAINER step (nerfstudio's scheduler_step_all), also for the group that is skipped on the
+    # iterations its networks run under no_grad: both groups sit at sched_step 400 although one took fewer updates
+    for name, opt in trainer.optimizers.items():
+        assert opt.sched_step == 400 or opt.sched_step == opt._last_sched_step + 1, name
+        assert opt._last_sched_step > 390, (name, opt._last_sched_step)
+        if opt.scheduler is not None:
+            assert opt.current_lr == pytest.approx(opt.scheduler.lr(opt._last_sched_step) * opt.lr / opt.scheduler.lr_init, rel=1e-6)
 
 
 def test_trained_model_matches_oracle(trained, cuda_device):
