@@ -126,11 +126,328 @@ def step_fn(field, batch, world, impl_id):
     return out, loss
 
 
-def run_ours(args):
+DTYPE = "f32 (parameters, gather, compositing and accumulators fp32; MLP products on tcgen05 as bf16 hi/lo splits, 3 MMAs per product, ~2^-16)"
+
+
+def _ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of ``kernel`` from the committed `ncu --set full` capture
+    (profiles/r2_ncu_traffic.json names the capture file of every entry); None when no capture of this kernel is committed."""
+    p = ROOT / "profiles" / "r2_ncu_traffic.json"
+    if not p.exists():
+        return None, None
+    j = json.loads(p.read_text()).get(kernel)
+    return (j["dram_bytes"], j["capture"]) if j else (None, None)
+
+
+def kernel_names(variant: str, kernel: str):
+    if kernel == "simt":
+        return "simt_field_forward_kernel + simt_composite_kernel", "simt_field_backward_kernel"
+    if variant == "small":
+        return "tc_render_forward_ws_kernel", "tc_field_backward_kernel"
+    return "tc_render_forward_big_kernel", "tc_big_backward_chain_kernel + tc_big_dw_kernel"
+
+
+def _stage(msg: str) -> None:
+    if os.environ.get("FNR_BENCH_DEBUG"):
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
+def measure_variant(variant: str, steps: int, warmup: int, args, world: int, rank: int, dev, impl_id, with_e2e: bool = True):
+    """Device-timed step / forward / backward and (optionally) the end-to-end loop of one field variant."""
     from fruitnerf_b200 import _lib as L
     from fruitnerf_b200 import ops
     from fruitnerf_b200 import synthetic as syn
-    from fruitnerf_b200.engine import GraphedTrainStep
+    from fruitnerf_b200.engine import GraphedTrainStep, default_loss
+
+    field = build_field(variant, dev)
+    N_pts = R_RAYS * S_SAMPLES
+    # per-rank batch (weak scaling: each rank draws its own 4096 rays, fruit_pipeline.py:97-99)
+    o, d, s, e, cam = syn.ray_batch(R_RAYS, S_SAMPLES, salt=rank, num_images=NUM_IMAGES)
+    img, mask = syn.targets(R_RAYS, salt=rank)
+    host = [t.pin_memory() for t in (o, d, s, e, cam.to(torch.int32), img, mask)]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    # the public training-step API: render fwd + loss + bwd captured in one CUDA graph
+    exchange = None
+    if world > 1:
+        from fruitnerf_b200.grad_exchange import make_gradient_exchange
+
+        # the exchange owns the flat gradient buffer (symmetric / multicast-mapped for the NVLS kernel): the backward kernels
+        # accumulate straight into it
+        exchange = make_gradient_exchange(ops.flat_grad_numel(field.kernel_params()), world, dev, kind=args.exchange)
+    step = GraphedTrainStep(field, R_RAYS, S_SAMPLES, impl=impl_id, use_graph=not args.no_graph,
+                            flat_grad=exchange.flat if exchange is not None else None)
+    h2d = step.load_batch(*host)
+    packed = step.pack_batch(*host)  # the same batch as one pinned byte buffer: one H2D copy per step in the e2e loop
+    _stage(f"{variant}: capture")
+    step.capture(warmup=max(warmup, 3))
+    _stage(f"{variant}: captured, warm-up")
+
+    def one_step():
+        loss = step()
+        if exchange is not None:
+            exchange()  # the reference's DDP exchange: mean of the gradients over ranks (fruit_pipeline.py:117)
+        return loss
+
+    for _ in range(max(warmup, 3)):
+        one_step()
+    torch.cuda.synchronize()
+
+    _stage(f"{variant}: timed loop")
+    sampler = ClockSampler(dev.index) if (rank == 0 and not args.no_clocks) else None
+    if sampler:
+        sampler.start()  # before the barrier: host work on rank 0 between the barrier and the first timed step would show up
+                         # as a long first step on the other ranks (they wait in the all-reduce)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(steps)]
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize()
+    for i in range(steps):
+        if not args.no_flush:
+            flush.fill_(float(i))  # evict the table / weights from L2 between timed steps
+        evs[i][0].record()
+        one_step()
+        evs[i][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    step_ms = [ev[0].elapsed_time(ev[1]) for ev in evs]
+    if os.environ.get("FNR_BENCH_DEBUG"):
+        print(f"rank {rank} {variant} step_ms " + " ".join(f"{v:.3f}" for v in step_ms), file=sys.stderr)
+    total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms)
+
+    # communication alone (N > 1): the exchange of the (static) flat gradient buffer, event-timed, max over ranks
+    comm_ms = None
+    if exchange is not None:
+        import torch.distributed as dist
+
+        cev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(10)]
+        dist.barrier()
+        for a_, b_ in cev:
+            a_.record()
+            exchange()
+            b_.record()
+        torch.cuda.synchronize()
+        c = torch.tensor([sum(a_.elapsed_time(b_) for a_, b_ in cev) / len(cev)], device=dev, dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.MAX)
+        comm_ms = float(c)
+
+    _stage(f"{variant}: phase graphs")
+    # phases, event-timed directly: graph A = forward + loss, graph B = backward (the same kernels as the one-graph step)
+    st = step.static
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+
+    def fwd_loss():
+        out = ops.render(field.kernel_shape(), field.kernel_params(), st["origins"], st["directions"], st["starts"], st["ends"],
+                         st["camera_indices"], field.position_mode(), field.appearance_mode(), impl=impl_id)
+        return out, default_loss(out, st["image"], st["fruit_mask"])
+
+    saved_grads = [p.grad for p in step.params]  # the step graph's static .grad views; restored below
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            for p in step.params:
+                p.grad = None
+            _, l_ = fwd_loss()
+            l_.backward()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    for p in step.params:
+        p.grad = None
+    _stage(f"{variant}: phase graphs warm, capturing")
+    gA, gB = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    # both captures on ONE stream: autograd runs a node's backward on the stream its forward ran on
+    with torch.cuda.graph(gA, stream=side):
+        _, loss_ab = fwd_loss()
+    with torch.cuda.graph(gB, pool=gA.pool(), stream=side):
+        loss_ab.backward()
+    _stage(f"{variant}: phase graphs captured, replaying")
+    pev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    for i in range(steps):
+        if not args.no_flush:
+            flush.fill_(float(i))
+        pev[i][0].record()
+        gA.replay()
+        pev[i][1].record()
+        gB.replay()
+        pev[i][2].record()
+    torch.cuda.synchronize()
+    fwd_loss_ms = sum(ev[0].elapsed_time(ev[1]) for ev in pev) / steps
+    bwd_ms = sum(ev[1].elapsed_time(ev[2]) for ev in pev) / steps
+    for p, g in zip(step.params, saved_grads):
+        p.grad = g
+
+    _stage(f"{variant}: forward-only graph")
+    # forward kernel alone (training forward: writes the encoding stash), for the roofline of the fused forward
+    fwd_graph = torch.cuda.CUDAGraph()
+
+    def fwd_only():
+        return ops.render(field.kernel_shape(), field.kernel_params(), st["origins"], st["directions"], st["starts"], st["ends"],
+                          st["camera_indices"], field.position_mode(), field.appearance_mode(), impl=impl_id)
+
+    with torch.no_grad():
+        with torch.cuda.graph(fwd_graph):
+            fwd_out = fwd_only()
+    fev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(steps)]
+    for i in range(steps):
+        if not args.no_flush:
+            flush.fill_(float(i))
+        fev[i][0].record()
+        fwd_graph.replay()
+        fev[i][1].record()
+    torch.cuda.synchronize()
+    fwd_ms = sum(ev[0].elapsed_time(ev[1]) for ev in fev) / steps
+    del fwd_out
+
+    # end-to-end through the public API with HOST buffers: per step H2D of the rays/targets from pinned
+    # memory, one graph replay, D2H read of the loss -- all inside the timed region
+    e2e = None
+    _stage(f"{variant}: e2e loop")
+    if with_e2e:
+        e2e_steps = max(steps, 20)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step.load_packed(packed)
+        for i in range(e2e_steps):
+            # H2D of the NEXT step's rays / bins / targets (one packed pinned buffer) overlaps this step, as a prefetching
+            # data loader does; every step still moves one full batch host->device and one loss device->host
+            step.prefetch_packed(packed)
+            loss = one_step()
+            _ = float(loss)  # D2H + sync
+            step.commit_prefetched()
+        torch.cuda.synchronize()
+        e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * R_RAYS * e2e_steps / float(e2e_s), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+               "steps": e2e_steps}
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+
+    _stage(f"{variant}: done")
+    peak, peak_src = _peaks()
+    mean_step = total_ms / steps
+    fwd_bytes = N_pts * HASH_BYTES_PER_POINT_FWD
+    bwd_bytes = N_pts * HASH_BYTES_PER_POINT_BWD
+    fwd_kernel, bwd_kernel = kernel_names(variant, args.kernel)
+    dominant_is_bwd = bwd_ms >= fwd_ms
+    traffic, traffic_src = _ncu_traffic(bwd_kernel.split(" + ")[0] if dominant_is_bwd else fwd_kernel.split(" + ")[0])
+
+    def roof(nbytes, ms, **extra):
+        ach = nbytes / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "launch_ms": ms,
+                "algorithmic_bytes_per_launch": nbytes, **extra}
+
+    res = {
+        "value": world * R_RAYS * steps / (total_ms * 1e-3),
+        "ms_per_step": mean_step,
+        "fwd_ms": fwd_ms,
+        "fwd_loss_ms": fwd_loss_ms,
+        "bwd_ms": bwd_ms,
+        "phase_timing": "fwd_ms: forward kernel alone; fwd_loss_ms / bwd_ms: forward + loss graph and backward graph replayed back to back, "
+                        "CUDA events between them (not derived by subtraction)",
+        "fwd_rays_per_s": R_RAYS / (fwd_ms * 1e-3),
+        "roofline": roof(bwd_bytes if dominant_is_bwd else fwd_bytes, bwd_ms if dominant_is_bwd else fwd_ms,
+                         kernel=(f"render backward ({bwd_kernel} + simt_composite_backward_kernel)" if dominant_is_bwd
+                                 else f"fused render forward ({fwd_kernel})"),
+                         traffic=traffic, traffic_source=traffic_src, peak_source=peak_src),
+        "roofline_forward": roof(fwd_bytes, fwd_ms, kernel=fwd_kernel),
+        "roofline_backward": roof(bwd_bytes, bwd_ms, kernel=bwd_kernel),
+        "roofline_step": roof(fwd_bytes + bwd_bytes, mean_step),
+        "gpu_launches_per_step": step.launches_per_step,
+        "clocks": clocks,
+    }
+    if comm_ms is not None:
+        res["comm_ms"] = comm_ms
+        res["exchange"] = exchange.describe()
+    if e2e is not None:
+        res["e2e"] = e2e
+    del step, field, flush
+    torch.cuda.empty_cache()
+    return res
+
+
+def measure_export(dev, n: int = 512, batch: int = 32768):
+    """BASELINE.json configs[4]: uniform n^3 volume sample of the fruit_nerf field through fnr_export_forward (field + the three
+    threshold selections + stream compaction per launch), batches of 32768 rays, deterministic grid.  Thresholds are taken from a
+    probe batch (random weights never reach the reference constants 70 / 3) so that all three sets are populated."""
+    from fruitnerf_b200 import _lib as L
+    from fruitnerf_b200 import ops
+    from fruitnerf_b200 import synthetic as syn
+    from fruitnerf_b200.fruit_field import FruitField
+
+    v = dict(syn.SMALL)
+    sd = syn.field_state(geo=v["geo"], sem_dims=v["sem_dims"], log2_hashmap_size=v["log2_hashmap_size"], num_images=7, table_scale=2.0,
+                         weight_gain=2.5)
+    field = FruitField(aabb=sd["aabb"], num_images=7, geo_feat_dim=v["geo"], max_res=v["max_res"], log2_hashmap_size=v["log2_hashmap_size"],
+                       num_layers_semantic=len(v["sem_dims"]) - 1, hidden_dim_semantics=v["sem_dims"][1], use_semantics=True,
+                       num_semantic_classes=1, test_mode="export", spatial_distortion=None)
+    field.load_state_dict(sd, strict=False)
+    field = field.to(dev).eval()
+    lin = torch.linspace(-1.0, 1.0, n)
+    gx, gy = torch.meshgrid(lin, lin, indexing="ij")  # fruit_datamanager.py:71-121 for the cube [-1,1]^3, x-major
+    pts = torch.stack([gx.reshape(-1), gy.reshape(-1), torch.full((n * n,), -1.0)], dim=-1).to(dev)
+    normal, far, total = (0.0, 0.0, 1.0), 2.0, n ** 3
+    bins = torch.linspace(0.0, 1.0, n + 1).to(dev)
+    shape, params = field.kernel_shape(), field.kernel_params()
+    mid = (n * n // 2 // 2048) * 2048
+    dense = ops.export_batch(shape, params, pts[mid:mid + 2048], normal, bins, 0.0, far, ops.ExportBuffers(capacity=1, device=dev), dense_out=True)
+    thr = (float(dense["semantics"].quantile(0.97)), float(dense["density"].quantile(0.97)), 0.5)
+    capacity = min(total, 1 << 25)
+
+    def run(count):
+        buf = ops.ExportBuffers(capacity=capacity, device=dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        torch.cuda.synchronize()
+        L.load().fnr_launch_count(1)
+        ev[0].record()
+        done = 0
+        while done < count:
+            o = pts[done:done + batch]
+            ops.export_batch(shape, params, o, normal, bins, 0.0, far, buf, point_base=done * n, dense_out=False, thresholds=thr)
+            done += o.shape[0]
+        ev[1].record()
+        torch.cuda.synchronize()
+        return ev[0].elapsed_time(ev[1]), buf, int(L.load().fnr_launch_count(1))
+
+    run(batch)  # warm-up
+    ms, buf, launches = min((run(pts.shape[0]) for _ in range(2)), key=lambda r: r[0])
+    counts = buf.counts.cpu().tolist()
+    keys = [buf.keys[k][: min(counts[k], capacity)] for k in range(3)]
+    ok = True
+    for k in range(3):  # size-independent properties: unique global keys inside the volume, semantic sets nested in the density set
+        u = torch.unique(keys[k])
+        ok &= bool(u.numel() == keys[k].numel()) and (keys[k].numel() == 0 or int(u.max()) < total)
+    s2 = torch.sort(keys[2]).values
+    for k in (0, 1):
+        if keys[k].numel():
+            pos = torch.searchsorted(s2, keys[k]).clamp_(max=max(s2.numel() - 1, 0))
+            ok &= bool((s2[pos] == keys[k]).all())
+    peak, _ = _peaks()
+    ach = total * HASH_BYTES_PER_POINT_FWD / (ms * 1e-3) / 1e9
+    return {"workload": f"uniform {n}^3 volume sample of the fruit_nerf field, {batch} rays x {n} samples per launch, deterministic grid",
+            "ms": ms, "points": total, "points_per_s": total / (ms * 1e-3), "counts": counts, "thresholds": thr,
+            "keys_unique_and_nested": bool(ok), "gpu_launches": launches,
+            "roofline": {"kernel": "tc_render_forward_ws_kernel<export>", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "algorithmic_bytes": total * HASH_BYTES_PER_POINT_FWD}}
+
+
+def run_ours(args):
+    from fruitnerf_b200 import _lib as L
 
     L.load()
     if not torch.cuda.is_available():
@@ -147,113 +464,25 @@ def run_ours(args):
 
         dist.init_process_group("nccl", device_id=dev)
     impl_id = {"auto": L.FNR_IMPL_AUTO, "simt": L.FNR_IMPL_SIMT, "tcgen05": L.FNR_IMPL_TCGEN05}[args.kernel]
-    field = build_field(args.variant, dev)
-    N_pts = R_RAYS * S_SAMPLES
-
-    # per-rank batch (weak scaling: each rank draws its own 4096 rays, fruit_pipeline.py:97-99)
-    o, d, s, e, cam = syn.ray_batch(R_RAYS, S_SAMPLES, salt=rank, num_images=NUM_IMAGES)
-    img, mask = syn.targets(R_RAYS, salt=rank)
-    host = [t.pin_memory() for t in (o, d, s, e, cam.to(torch.int32), img, mask)]
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
-
-    # the public training-step API: render fwd + loss + bwd captured in one CUDA graph
-    step = GraphedTrainStep(field, R_RAYS, S_SAMPLES, impl=impl_id, use_graph=not args.no_graph)
-    h2d = step.load_batch(*host)
-    packed = step.pack_batch(*host)  # the same batch as one pinned byte buffer: one H2D copy per step in the e2e loop
-    step.capture(warmup=max(args.warmup, 3))
-
-    def one_step():
-        loss = step()
-        if world > 1:
-            import torch.distributed as dist
-
-            dist.all_reduce(step.flat_grad, op=dist.ReduceOp.AVG)  # the reference's DDP exchange
-        return loss
-
-    for _ in range(max(args.warmup, 3)):
-        one_step()
-    torch.cuda.synchronize()
-
-    sampler = ClockSampler(local) if (rank == 0 and not args.no_clocks) else None
-    if sampler:
-        sampler.start()  # before the barrier: host work on rank 0 between the barrier and the first timed step would show up
-                         # as a long first step on the other ranks (they wait in the all-reduce)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.barrier()
-    torch.cuda.synchronize()
-    for i in range(args.steps):
-        if not args.no_flush:
-            flush.fill_(float(i))  # evict the table / weights from L2 between timed steps
-        evs[i][0].record()
-        one_step()
-        evs[i][1].record()
-    torch.cuda.synchronize()
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.barrier()
-    clocks = sampler.stop() if sampler else None
-    step_ms = [ev[0].elapsed_time(ev[1]) for ev in evs]
-    if os.environ.get("FNR_BENCH_DEBUG"):
-        print(f"rank {rank} step_ms " + " ".join(f"{v:.3f}" for v in step_ms), file=sys.stderr)
-    total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms)
-
-    # forward kernel alone (training forward: writes the encoding stash), for the roofline of the fused forward
-    st = step.static
-    fwd_graph = torch.cuda.CUDAGraph()
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-
-    def fwd_only():
-        return ops.render(field.kernel_shape(), field.kernel_params(), st["origins"], st["directions"], st["starts"], st["ends"],
-                          st["camera_indices"], field.position_mode(), field.appearance_mode(), impl=impl_id)
-
-    with torch.cuda.stream(side):
-        fwd_only()
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    with torch.cuda.graph(fwd_graph):
-        fwd_out = fwd_only()
-    fev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
-    for i in range(args.steps):
-        if not args.no_flush:
-            flush.fill_(float(i))
-        fev[i][0].record()
-        fwd_graph.replay()
-        fev[i][1].record()
-    torch.cuda.synchronize()
-    fwd_ms = [ev[0].elapsed_time(ev[1]) for ev in fev]
-    del fwd_out
-
-    # end-to-end through the public API with HOST buffers: per step H2D of the rays/targets from pinned
-    # memory, one graph replay, D2H read of the loss -- all inside the timed region
-    e2e_steps = max(args.steps, 20)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    step.load_packed(packed)
-    for i in range(e2e_steps):
-        # H2D of the NEXT step's rays / bins / targets (one packed pinned buffer) overlaps this step, as a prefetching
-        # data loader does; every step still moves one full batch host->device and one loss device->host
-        step.prefetch_packed(packed)
-        loss = one_step()
-        _ = float(loss)  # D2H + sync
-        step.commit_prefetched()
-    torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_s)
-
+    warm = max(args.warmup, 3)
+    head = measure_variant(args.variant, args.steps, warm, args, world, rank, dev, impl_id)
+    variants = {}
+    if args.variant == "small" and not args.no_variants:
+        # BASELINE.json configs[2] / [3]: fruit_nerf_big, same batch shape, same timing rules (fewer timed steps)
+        try:
+            b = measure_variant("big", max(3, min(args.steps, 10)), 3, args, world, rank, dev, impl_id)
+            b["config"] = {"workload": f"fruit_nerf_big field: {R_RAYS} rays x {S_SAMPLES} samples per GPU, render fwd + MSE/BCE loss + bwd"
+                                       + (" + gradient exchange" if world > 1 else ""), "steps": max(3, min(args.steps, 10)), "warmup": 3}
+            b.pop("clocks", None)
+            variants["big"] = b
+        except Exception as ex:  # noqa: BLE001 -- never allowed to break the headline line
+            variants["big"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+    export = None
+    if world == 1 and not args.no_variants:
+        try:
+            export = measure_export(dev)
+        except Exception as ex:  # noqa: BLE001
+            export = {"error": f"{type(ex).__name__}: {ex}"[:300]}
     if world > 1:
         import torch.distributed as dist
 
@@ -261,36 +490,22 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank != 0:
         return
-    peak, peak_src = _peaks()
-    mean_step = total_ms / args.steps
-    mean_fwd = sum(fwd_ms) / len(fwd_ms)
-    mean_bwd = max(mean_step - mean_fwd, 1e-6)
-    fwd_bytes = N_pts * HASH_BYTES_PER_POINT_FWD
-    bwd_bytes = N_pts * HASH_BYTES_PER_POINT_BWD
-    fwd_ach = fwd_bytes / (mean_fwd * 1e-3) / 1e9
-    bwd_ach = bwd_bytes / (mean_bwd * 1e-3) / 1e9
-    dominant_is_bwd = mean_bwd >= mean_fwd
-    on_tc = args.variant == "small" and args.kernel != "simt"  # the families the tcgen05 kernels serve (fnr_api.cu dispatch)
-    fwd_kernel = ("tc_render_forward_kernel" if on_tc else
-                  "tc_render_forward_big_kernel" if args.kernel != "simt" else "simt_field_forward_kernel + simt_composite_kernel")
-    bwd_kernel = ("tc_field_backward_kernel" if on_tc else
-                  "tc_big_backward_chain_kernel + cuBLAS dW GEMMs" if args.kernel != "simt" else "simt_field_backward_kernel")
     line = {
         "metric": "rays/sec (4096 rays x 192 samples) fused fwd+bwd",
-        "value": world * R_RAYS * args.steps / (total_ms * 1e-3),
+        "value": head["value"],
         "unit": "rays/s",
         "n_gpus": world,
         "steps": args.steps,
-        "warmup": max(args.warmup, 3),
-        "ms_per_step": mean_step,
+        "warmup": warm,
+        "ms_per_step": head["ms_per_step"],
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
-        "dtype": "f32",
+        "dtype": DTYPE,
         "data": "synthetic",
         "config": {
             "workload": f"fruit_nerf{'_big' if args.variant == 'big' else ''} field ({args.variant}): {R_RAYS} rays x {S_SAMPLES} samples "
-                        "per GPU, render fwd + MSE/BCE loss + bwd" + (" + NCCL grad all-reduce" if world > 1 else ""),
+                        "per GPU, render fwd + MSE/BCE loss + bwd" + (" + gradient exchange (mean over ranks)" if world > 1 else ""),
             "variant": args.variant,
             "kernel": args.kernel,
             "rays_per_gpu": R_RAYS,
@@ -299,35 +514,21 @@ def run_ours(args):
             "l2": "flushed between timed steps (256 MiB fill); per-step CUDA-event durations summed",
             "parallelism": f"dp{world}",
         },
-        "fwd_ms": mean_fwd,
-        "bwd_ms": mean_bwd,
-        "fwd_rays_per_s": R_RAYS / (mean_fwd * 1e-3),
-        "roofline": {
-            "kernel": (f"render backward ({bwd_kernel} + simt_composite_backward_kernel + loss)" if dominant_is_bwd
-                       else f"fused render forward ({fwd_kernel})"),
-            "bound": "hbm",
-            "achieved": bwd_ach if dominant_is_bwd else fwd_ach,
-            "peak": peak,
-            "unit": "GB/s",
-            "frac": (bwd_ach if dominant_is_bwd else fwd_ach) / peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-            # `ncu --set full` capture (profiles/r1_ncu_summary.md, final round-1 tables); small variant only
-            "traffic": (NCU_DRAM_BYTES["bwd" if dominant_is_bwd else "fwd"] if on_tc else None),
-            "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": bwd_bytes if dominant_is_bwd else fwd_bytes,
-            "launch_ms": mean_bwd if dominant_is_bwd else mean_fwd,
-        },
-        "roofline_forward": {"kernel": fwd_kernel, "bound": "hbm", "achieved": fwd_ach, "peak": peak, "unit": "GB/s",
-                             "frac": fwd_ach / peak, "launch_ms": mean_fwd, "algorithmic_bytes_per_launch": fwd_bytes},
-        "roofline_step": {"bound": "hbm", "achieved": (fwd_bytes + bwd_bytes) / (mean_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                          "frac": (fwd_bytes + bwd_bytes) / (mean_step * 1e-3) / 1e9 / peak},
-        "e2e": {"value": world * R_RAYS * e2e_steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "steps": e2e_steps},
-        "gpu_launches": 3 * args.steps,
-        "clocks": clocks,
     }
+    for k in ("fwd_ms", "fwd_loss_ms", "bwd_ms", "phase_timing", "fwd_rays_per_s", "roofline", "roofline_forward", "roofline_backward", "roofline_step",
+              "e2e", "comm_ms", "exchange", "clocks"):
+        if k in head:
+            line[k] = head[k]
+    # kernels of THIS library launched inside the timed region: counted by the library itself (fnr_launch_count) while the step
+    # was captured into its CUDA graph, times the replays that were timed
+    line["gpu_launches"] = int(head["gpu_launches_per_step"]) * args.steps
+    line["gpu_launches_per_step"] = int(head["gpu_launches_per_step"])
+    if variants:
+        line["variants"] = variants
+    if export is not None:
+        line["export_512"] = export
     if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline(args.variant, sample_rays=args.cpu_rays, repeats=1)
+        line["cpu_baseline"] = cpu_baseline(args.variant, sample_rays=args.cpu_rays, repeats=3)
     if world == 1 and not args.no_train:
         line["train_iteration"] = train_iteration_rate(args.variant, dev)
     print(json.dumps(line))
@@ -357,25 +558,30 @@ def train_iteration_rate(variant: str, dev, iterations: int = 300):
         return {"error": f"{type(ex).__name__}: {ex}"[:300]}
 
 
-# per-launch DRAM traffic measured by ncu (profiles/r1_ncu_summary.md): tc_render_forward_kernel 57.9 MB read + 87.2 MB
-# written; tc_field_backward_kernel 176.9 MB read + 19.7 MB written.  Far below the algorithmic hash bytes because the
-# 64 MiB fruit_nerf table is L2-resident.
-NCU_DRAM_BYTES = {"fwd": 57_898_240 + 87_247_360, "bwd": 176_867_840 + 19_650_816}
+def host_threads() -> int:
+    """Threads of the CPU arm: every host core the process may use (torchrun sets OMP_NUM_THREADS=1, which would
+    otherwise make the reference arm single-threaded at N > 1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, n)
 
 
 def cpu_baseline(variant: str, sample_rays: int, repeats: int):
     """The oracle (a port: pure-PyTorch restatement of the reference's CPU-runnable torch path) on
-    the host cores, fwd+bwd on a bounded sample of the same workload."""
+    the host cores, fwd+bwd on the same workload: median of ``repeats`` passes after one warm-up pass."""
     from fruitnerf_b200 import synthetic as syn
     from oracle import fruit_ref as fr
 
+    torch.set_num_threads(host_threads())
     v = syn.SMALL if variant == "small" else syn.BIG
     sd = syn.field_state(geo=v["geo"], sem_dims=v["sem_dims"], log2_hashmap_size=v["log2_hashmap_size"], num_images=NUM_IMAGES,
                          table_scale=1e-1)
     spec = fr.FieldSpec(max_res=v["max_res"], log2_hashmap_size=v["log2_hashmap_size"], geo_feat_dim=v["geo"])
     o, d, s, e, cam = syn.ray_batch(sample_rays, S_SAMPLES, num_images=NUM_IMAGES)
     img, mask = syn.targets(sample_rays)
-    best = None
+    times = []
     for _ in range(repeats + 1):  # first pass = warm-up
         st = {k: t.clone().requires_grad_(t.is_floating_point() and k != "aabb") for k, t in sd.items()}
         t0 = time.perf_counter()
@@ -383,52 +589,55 @@ def cpu_baseline(variant: str, sample_rays: int, repeats: int):
         r = fr.render(f, s[..., None], e[..., None], training=True)
         ld = fr.loss_dict(r, img, mask)
         (ld["rgb_loss"] + ld["semantics_loss"]).backward()
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return {"value": sample_rays / best, "unit": "rays/s", "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": "port",
-            "sample": f"{sample_rays} rays x {S_SAMPLES} samples of the same workload, fwd+bwd, best of {repeats} after 1 warm-up"}
+        times.append(time.perf_counter() - t0)
+    timed = sorted(times[1:]) if repeats else times
+    med = timed[len(timed) // 2]
+    return {"value": sample_rays / med, "unit": "rays/s", "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": "port",
+            "seconds": [round(t, 3) for t in times[1:] if repeats] or [round(times[0], 3)],
+            "sample": f"{sample_rays} rays x {S_SAMPLES} samples ({'the full batch' if sample_rays == R_RAYS else 'a sample'} of the same workload), "
+                      f"fwd+bwd, median of {max(repeats, 1)} after 1 warm-up, torch.set_num_threads({torch.get_num_threads()})"}
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  The reference's
     arithmetic lives in nerfstudio/tinycudann (absent, not installable: BASELINE.md section 2), so
-    the arm is the oracle port on all host threads; each step = a bounded sample of the workload."""
+    the arm is the oracle port on all host threads; each step = one pass over the 4096-ray batch."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     rays = args.cpu_rays
-    vals = []
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_baseline(args.variant, rays, repeats=0)
+    n = max(1, min(args.steps, 3))
     t_all = time.perf_counter()
-    for _ in range(max(1, min(args.steps, 3))):
-        vals.append(cpu_baseline(args.variant, rays, repeats=0))
+    base = cpu_baseline(args.variant, rays, repeats=n)
     dt = time.perf_counter() - t_all
-    v = sum(x["value"] for x in vals) / len(vals)
+    v = base["value"]
     line = {
         "impl": "reference",
         "metric": "rays/sec (4096 rays x 192 samples) fused fwd+bwd",
         "value": v,
         "unit": "rays/s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-        "steps": len(vals),
+        "steps": n,
         "warmup": 1,
-        "ms_per_step": dt / len(vals) * 1e3,
+        "ms_per_step": rays / v * 1e3,
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"fruit_nerf field ({args.variant}): {rays}-ray x {S_SAMPLES}-sample sample of the 4096x192 batch, fwd+bwd, CPU",
-                   "variant": args.variant},
-        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{rays} rays x {S_SAMPLES} samples per step"},
+        "config": {"workload": f"fruit_nerf field ({args.variant}): {rays} rays x {S_SAMPLES} samples, fwd+bwd, CPU oracle port "
+                               f"({base['cores']} threads), median of {n} passes", "variant": args.variant, "wall_s": round(dt, 1)},
+        "cpu_baseline": base,
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
 def main():
+    if os.environ.get("FNR_BENCH_DEBUG"):
+        import faulthandler
+
+        faulthandler.dump_traceback_later(int(os.environ.get("FNR_BENCH_WATCHDOG", "60")), exit=False)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -436,9 +645,12 @@ def main():
     ap.add_argument("--variant", default="small", choices=["small", "big"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05"])
-    ap.add_argument("--cpu-rays", type=int, default=2048)
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "nvls", "nvls_bf16"],
+                    help="gradient exchange at N > 1: NCCL all-reduce or the library's own multimem (NVLS) all-reduce kernel")
+    ap.add_argument("--cpu-rays", type=int, default=R_RAYS)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the supplementary whole-training-iteration measurement")
+    ap.add_argument("--no-variants", action="store_true", help="skip the fruit_nerf_big and 512^3 export measurements")
     ap.add_argument("--no-graph", action="store_true", help="diagnostic: eager step instead of the CUDA-graph step")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic: skip the L2 flush between timed steps")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample nvidia-smi during the timed region")

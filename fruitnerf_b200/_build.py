@@ -8,7 +8,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "libfruitnerf_b200.so"
-SOURCES = ["fnr_api.cu", "fnr_simt.cu", "fnr_tc.cu", "fnr_tc_ws.cu", "fnr_tc_big.cu", "fnr_tc_big_bwd.cu", "fnr_tc_bwd.cu", "fnr_proposal.cu", "fnr_optim.cu", "fnr_glue.cu"]
+SOURCES = ["fnr_api.cu", "fnr_simt.cu", "fnr_tc.cu", "fnr_tc_ws.cu", "fnr_tc_big.cu", "fnr_tc_big_bwd.cu", "fnr_tc_bwd.cu", "fnr_proposal.cu", "fnr_optim.cu", "fnr_glue.cu", "fnr_nvls.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",

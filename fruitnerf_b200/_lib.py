@@ -123,6 +123,21 @@ class ExportParams(C.Structure):
     ]
 
 
+class NvlsDesc(C.Structure):
+    _fields_ = [
+        ("multicast_ptr", C.c_void_p),
+        ("local_ptr", C.c_void_p),
+        ("multicast_bf16", C.c_void_p),
+        ("local_bf16", C.c_void_p),
+        ("signal_pads", C.c_void_p),
+        ("grid_counter", C.c_void_p),
+        ("rank", C.c_int32),
+        ("world_size", C.c_int32),
+        ("signal_slots", C.c_int32),
+        ("signal_slot_base", C.c_int32),
+    ]
+
+
 class ExportOut(C.Structure):
     _fields_ = [
         ("rows", C.c_void_p * 3),
@@ -163,6 +178,8 @@ LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libfruitnerf_b200.so"
 # every symbol include/fruitnerf_b200.h declares
 EXPORTED_SYMBOLS = (
     "fnr_version",
+    "fnr_launch_count",
+    "fnr_nvls_allreduce_mean",
     "fnr_last_error",
     "fnr_render_forward",
     "fnr_render_backward",
@@ -202,6 +219,10 @@ def load() -> C.CDLL:
         )
     lib = C.CDLL(str(path))
     lib.fnr_version.restype = C.c_int
+    lib.fnr_nvls_allreduce_mean.restype = C.c_int
+    lib.fnr_nvls_allreduce_mean.argtypes = [C.POINTER(NvlsDesc), C.c_size_t, C.c_int32, C.c_void_p]
+    lib.fnr_launch_count.restype = C.c_uint64
+    lib.fnr_launch_count.argtypes = [C.c_int32]
     lib.fnr_last_error.restype = C.c_char_p
     lib.fnr_render_forward.restype = C.c_int
     lib.fnr_render_forward.argtypes = [C.POINTER(FieldDesc), C.POINTER(FieldParams), C.POINTER(RayBatch), C.POINTER(RenderOut), C.c_void_p]

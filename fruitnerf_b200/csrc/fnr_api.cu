@@ -2,6 +2,7 @@
 // structs of include/fruitnerf_b200.h into kernel arguments, dispatch between the fused tcgen05
 // kernels and the fp32 simt kernels.  No host synchronisation, no allocation (the one exception: the cuBLAS handle the
 // big-family backward creates at its first call, fnr_tc_big_bwd.cu).
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -23,6 +24,13 @@ int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return FNR_OK;
   set_error("CUDA error in %s: %s", what, cudaGetErrorString(e));
   return FNR_ERR_CUDA;
+}
+
+// every kernel launch of the library ends here: launch counter (fnr_launch_count) + launch-error check
+static std::atomic<unsigned long long> g_launches{0};
+int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_cuda(cudaGetLastError(), what);
 }
 
 static bool mlp_is(const fnr_mlp_desc& m, int n, const int* dims) {
@@ -164,6 +172,10 @@ using namespace fnr;
 extern "C" {
 
 int fnr_version(void) { return FNR_ABI_VERSION; }
+
+uint64_t fnr_launch_count(int32_t reset) {
+  return reset ? fnr::g_launches.exchange(0, std::memory_order_relaxed) : fnr::g_launches.load(std::memory_order_relaxed);
+}
 
 const char* fnr_last_error(void) { return g_error; }
 

@@ -159,6 +159,7 @@ __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf
 // host-side error plumbing -------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
+int check_launch(const char* what);  // after every <<<>>>: counts the launch, then cudaGetLastError
 
 // Shape families the kernels are specialised for.
 //   SMALL: geo 15, semantic 15->64->64,        colour 63->64->64->3   (fruit_nerf)

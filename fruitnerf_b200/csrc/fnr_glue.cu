@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(kThreads) ray_metrics_kernel(KRayMetrics A) {
 int launch_pixel_batch(const KPixelBatch& A, cudaStream_t st) {
   if (A.R == 0) return FNR_OK;
   pixel_batch_kernel<<<(A.R + kThreads - 1) / kThreads, kThreads, 0, st>>>(A);
-  return check_cuda(cudaGetLastError(), "pixel_batch_kernel");
+  return check_launch("pixel_batch_kernel");
 }
 
 int launch_spaced_bins(const KSpacedBins& A, cudaStream_t st) {
@@ -196,12 +196,12 @@ int launch_spaced_bins(const KSpacedBins& A, cudaStream_t st) {
   long long blocks = (total + kThreads - 1) / kThreads;
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   spaced_bins_kernel<<<(int)blocks, kThreads, 0, st>>>(A);
-  return check_cuda(cudaGetLastError(), "spaced_bins_kernel");
+  return check_launch("spaced_bins_kernel");
 }
 
 int launch_render_losses(const KLosses& A, cudaStream_t st) {
   render_losses_kernel<<<1, 1024, 0, st>>>(A);
-  return check_cuda(cudaGetLastError(), "render_losses_kernel");
+  return check_launch("render_losses_kernel");
 }
 
 int launch_ray_metrics(const KRayMetrics& A, cudaStream_t st) {
@@ -211,7 +211,7 @@ int launch_ray_metrics(const KRayMetrics& A, cudaStream_t st) {
   int blocks = (A.R + wpb - 1) / wpb;
   if (blocks > sm_count() * 4) blocks = sm_count() * 4;
   ray_metrics_kernel<<<blocks, kThreads, smem, st>>>(A);
-  return check_cuda(cudaGetLastError(), "ray_metrics_kernel");
+  return check_launch("ray_metrics_kernel");
 }
 
 }  // namespace fnr

@@ -79,7 +79,7 @@ int launch_adam(const KAdam& A, int radam, const float* hyper, cudaStream_t st) 
     adam_kernel<true><<<(int)blocks, kThreads, 0, st>>>(A, hyper);
   else
     adam_kernel<false><<<(int)blocks, kThreads, 0, st>>>(A, hyper);
-  return check_cuda(cudaGetLastError(), "adam_kernel");
+  return check_launch("adam_kernel");
 }
 
 }  // namespace fnr

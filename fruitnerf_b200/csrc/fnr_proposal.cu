@@ -429,7 +429,7 @@ int grid_for_rays(int R) {
 int launch_proposal_weights_forward(const KDensity& D, const KRays& Rr, float* density, float* weights, cudaStream_t st) {
   if (Rr.R == 0) return FNR_OK;
   proposal_weights_forward_kernel<<<grid_for_rays(Rr.R), 32 * kWarpsPerBlock, 0, st>>>(D, Rr, density, weights);
-  return check_cuda(cudaGetLastError(), "proposal_weights_forward_kernel");
+  return check_launch("proposal_weights_forward_kernel");
 }
 
 int launch_proposal_weights_backward(const KDensity& D, const KDensity& G, const KRays& Rr, const float* density, const float* weights,
@@ -438,19 +438,19 @@ int launch_proposal_weights_backward(const KDensity& D, const KDensity& G, const
   int grid = grid_for_rays(Rr.R);
   if (grid > sm_count() * 4) grid = sm_count() * 4;
   proposal_weights_backward_kernel<<<grid, 32 * kWarpsPerBlock, 0, st>>>(D, G, Rr, density, weights, d_weights);
-  return check_cuda(cudaGetLastError(), "proposal_weights_backward_kernel");
+  return check_launch("proposal_weights_backward_kernel");
 }
 
 int launch_pdf_sample(const KPdf& A, cudaStream_t st) {
   if (A.R == 0) return FNR_OK;
   pdf_sample_kernel<<<grid_for_rays(A.R), 32 * kWarpsPerBlock, 0, st>>>(A);
-  return check_cuda(cudaGetLastError(), "pdf_sample_kernel");
+  return check_launch("pdf_sample_kernel");
 }
 
 int launch_interlevel_loss(const KInterlevel& A, cudaStream_t st) {
   if (A.R == 0) return FNR_OK;
   interlevel_loss_kernel<<<grid_for_rays(A.R), 32 * kWarpsPerBlock, 0, st>>>(A);
-  return check_cuda(cudaGetLastError(), "interlevel_loss_kernel");
+  return check_launch("interlevel_loss_kernel");
 }
 
 int proposal_limits(int* max_levels, int* hidden, int* max_bins) {

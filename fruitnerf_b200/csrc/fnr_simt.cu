@@ -817,21 +817,21 @@ int launch_simt_field_forward(Family fam, const KField& F, const KParams& P, con
     simt_field_forward_kernel<CfgSmall><<<grid, kThreads, 0, st>>>(F, P, Rr, O);
   else
     simt_field_forward_kernel<CfgBig><<<grid, kThreads, 0, st>>>(F, P, Rr, O);
-  return check_cuda(cudaGetLastError(), "simt_field_forward_kernel");
+  return check_launch("simt_field_forward_kernel");
 }
 
 int launch_simt_composite(const KRays& Rr, const KComposite& Cm, cudaStream_t st) {
   if (Rr.R == 0) return FNR_OK;
   const int grid = grid_for(Rr.R, kThreads / 32, sm_count() * 16);
   simt_composite_kernel<<<grid, kThreads, 0, st>>>(Rr, Cm);
-  return check_cuda(cudaGetLastError(), "simt_composite_kernel");
+  return check_launch("simt_composite_kernel");
 }
 
 int launch_simt_composite_backward(const KRays& Rr, const KCompositeBwd& B, cudaStream_t st) {
   if (Rr.R == 0) return FNR_OK;
   const int grid = grid_for(Rr.R, kThreads / 32, sm_count() * 16);
   simt_composite_backward_kernel<<<grid, kThreads, 0, st>>>(Rr, B);
-  return check_cuda(cudaGetLastError(), "simt_composite_backward_kernel");
+  return check_launch("simt_composite_backward_kernel");
 }
 
 template <class C>
@@ -848,7 +848,7 @@ static int launch_bwd(const KField& F, const KParams& P, const KParams& G, const
   const long long N = (long long)Rr.R * Rr.S;
   const int grid = grid_for(N, kThreads, sm_count() * 2);
   simt_field_backward_kernel<C><<<grid, kThreads, smem, st>>>(F, P, G, Rr, B);
-  return check_cuda(cudaGetLastError(), "simt_field_backward_kernel");
+  return check_launch("simt_field_backward_kernel");
 }
 
 int launch_simt_field_backward(Family fam, const KField& F, const KParams& P, const KParams& G, const KRays& Rr,
@@ -865,7 +865,7 @@ int launch_simt_export(Family fam, const KField& F, const KParams& P, const KExp
     simt_export_kernel<CfgSmall><<<grid, kThreads, 0, st>>>(F, P, E);
   else
     simt_export_kernel<CfgBig><<<grid, kThreads, 0, st>>>(F, P, E);
-  return check_cuda(cudaGetLastError(), "simt_export_kernel");
+  return check_launch("simt_export_kernel");
 }
 
 int launch_hash_indices(const KField& F, const KRays& Rr, int32_t* rows, float* positions, cudaStream_t st) {
@@ -873,7 +873,7 @@ int launch_hash_indices(const KField& F, const KRays& Rr, int32_t* rows, float* 
   if (N == 0) return FNR_OK;
   const int grid = grid_for(N, kThreads, sm_count() * 16);
   hash_indices_kernel<<<grid, kThreads, 0, st>>>(F, Rr, rows, positions);
-  return check_cuda(cudaGetLastError(), "hash_indices_kernel");
+  return check_launch("hash_indices_kernel");
 }
 
 }  // namespace fnr

@@ -480,7 +480,7 @@ int launch_tc_render_forward(Family fam, const KField& F, const KParams& P, cons
   const int groups = (Rr.R + a.rays_per_group - 1) / a.rays_per_group;
   const int grid = groups < sm_count() ? groups : sm_count();
   tc_render_forward_kernel<false><<<grid, kCtaThreads, kSmemBytes, st>>>(a);
-  return check_cuda(cudaGetLastError(), "tc_render_forward_kernel");
+  return check_launch("tc_render_forward_kernel");
 }
 
 // The export path reuses the fused forward (AABB positions, mean appearance embedding) and replaces the
@@ -505,7 +505,7 @@ int launch_tc_export(Family fam, const KField& F, const KParams& P, const KExpor
   const int groups = (E.B + a.rays_per_group - 1) / a.rays_per_group;
   const int grid = groups < sm_count() ? groups : sm_count();
   tc_render_forward_kernel<true><<<grid, kCtaThreads, kSmemBytes, st>>>(a);
-  return check_cuda(cudaGetLastError(), "tc_render_forward_kernel<export>");
+  return check_launch("tc_render_forward_kernel<export>");
 }
 
 }  // namespace fnr

@@ -400,7 +400,7 @@ int launch_tc_render_forward_big(const KField& F, const KParams& P, const KRays&
   const int groups = (Rr.R + a.rays_per_group - 1) / a.rays_per_group;
   const int grid = groups < sm_count() ? groups : sm_count();
   tc_render_forward_big_kernel<false><<<grid, kCtaThreads, kSmemBytes, st>>>(a);
-  return check_cuda(cudaGetLastError(), "tc_render_forward_big_kernel");
+  return check_launch("tc_render_forward_big_kernel");
 }
 
 int launch_tc_export_big(const KField& F, const KParams& P, const KExport& E, cudaStream_t st) {
@@ -417,7 +417,7 @@ int launch_tc_export_big(const KField& F, const KParams& P, const KExport& E, cu
   const int groups = (E.B + a.rays_per_group - 1) / a.rays_per_group;
   const int grid = groups < sm_count() ? groups : sm_count();
   tc_render_forward_big_kernel<true><<<grid, kCtaThreads, kSmemBytes, st>>>(a);
-  return check_cuda(cudaGetLastError(), "tc_render_forward_big_kernel<export>");
+  return check_launch("tc_render_forward_big_kernel<export>");
 }
 
 }  // namespace fnr

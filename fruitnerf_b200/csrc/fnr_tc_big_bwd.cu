@@ -1,17 +1,19 @@
-// Backward of the fruit_nerf_big family on the tensor cores, in two stages:
+// Backward of the fruit_nerf_big family on the tensor cores, in two kernels of this library (no cuBLAS):
 //   1. tc_big_backward_chain_kernel: per 128-point tile, recompute the activations from the stashed encoding (4 GEMM round
 //      trips, bit-identical to fnr_tc_big.cu, ReLU masks kept as register bitmasks), then back-propagate dY through the
 //      colour / semantic / base MLPs (dX = dY W with the forward weight tiles read MN-major, A operands in tensor memory),
 //      scatter the encoding gradient into the hash-table gradient and the appearance-embedding gradient -- and write every
-//      layer's input X (with a constant-1 column) and pre-activation gradient dY as fp32 row-major matrices to scratch.
-//   2. the weight / bias gradients dW = dY^T [X | 1] are plain GEMMs with the 786 k points as reduction dimension: they are
-//      handed to cuBLAS (TF32 tensor cores, resolved with dlopen so the library has no link-time dependency), followed by
-//      one unpack kernel that adds the products into the torch-layout gradient tensors (column permutation of the colour
-//      input, the folded semantic tail: d W_sem2 = head_w (x) v, d head_w = W_sem2 v + b_sem2 s, ...).
-// The 128-wide semantic layers make TMEM-resident dW accumulators (fnr_tc_bwd.cu) impossible here: 416 accumulator columns
-// plus the 384 columns of the chain exceed the 512 available.  Scratch: ~4.4 KB per point.
-#include <cublas_v2.h>
-#include <dlfcn.h>
+//      layer's input X and pre-activation gradient dY to scratch AS THE OPERAND TILES OF THE WEIGHT-GRADIENT GEMMS: bf16 hi / lo
+//      splits (the same packed words the thread just wrote to tensor memory) in the canonical core-matrix layout
+//      [8-feature chunk][64 points][16 B], grouped into four stage blocks per 64-point record (layout below).
+//   2. tc_big_dw_kernel: the weight / bias gradients dW = dY^T X, reduction over all points.  Persistent, one CTA per SM: a
+//      producer thread streams the stage blocks with TMA bulk copies (cp.async.bulk global -> shared, mbarrier complete_tx) into
+//      a two-slot shared-memory ring, an MMA thread issues tcgen05.mma straight on the landed tiles (both operands MN-major,
+//      K = points; hi*hi + lo*hi + hi*lo), and ALL accumulators (448 tensor-memory columns) stay resident for the whole kernel;
+//      they are flushed once per CTA with atomics into the torch-layout gradient tensors.  big_fold_kernel finishes the folded
+//      semantic tail (d W_sem2 = head_w (x) v, d head_w = W_sem2 v + b_sem2 s, ...).
+// The 128-wide semantic layers make accumulators resident in the CHAIN kernel (fnr_tc_bwd.cu) impossible here: 448 accumulator
+// columns plus the 384 columns of the chain exceed the 512 available.  Scratch: 4.3 KB per point.
 #include <cstdlib>
 #include "fnr_common.cuh"
 #include "fnr_kernels.h"
@@ -62,22 +64,29 @@ static_assert(kSmemBytes <= 227 * 1024, "shared-memory budget");
 
 constexpr int R_A0 = 0, R_A1 = 128, R_D0 = 256, R_D1 = 384;
 
-// scratch matrices (fp32, row-major, one row per point); X widths include the constant-1 column (+ padding to 4 floats)
-// every width is a multiple of 8 floats so that each thread writes whole 32-byte sectors (st.global.v8.f32);
-// layouts: XE [enc 32 | 1 | 0..], XH [h 64 | 1 | ..], XG [h0-slot, geo 30, pad | 1 | ..] (the kernel's K order),
-// XZ [z 128 | 1 | ..], XC [sh 16 | app 32 | h0-slot, geo 30, pad | 1 | ..] (kernel K order; big_unpack_kernel permutes)
-constexpr int XW_E = 40, XW_H = 72, XW_G = 40, XW_Z = 136, XW_C = 88, XW_C1 = 72, XW_C2 = 72;
-constexpr int DW_H = 64, DW_OUT = 32, DW_Z = 128, DW_C = 64, DW_R = 8;
-constexpr int kFloatsPerPoint = XW_E + XW_H + XW_G + 2 * XW_Z + XW_C + XW_C1 + XW_C2 + DW_H + DW_OUT + 2 * DW_Z + 2 * DW_C + DW_R;
-// GEMM outputs C_l [N_l x XW_l]
-constexpr int CO_B0 = 0, CO_B1 = CO_B0 + 64 * XW_E, CO_S0 = CO_B1 + 32 * XW_H, CO_S1 = CO_S0 + 128 * XW_G, CO_F = CO_S1 + 128 * XW_Z,
-              CO_C0 = CO_F + 4 * XW_Z, CO_C1 = CO_C0 + 64 * XW_C, CO_C2 = CO_C1 + 64 * XW_C1, CO_END = CO_C2 + 4 * XW_C2;
-
-struct Bufs {
-  float *xe, *xh, *xg, *xz1, *xz2, *xc, *xc1, *xc2;
-  float *dh, *dout, *dz1, *dz2, *dc1, *dc2, *dr;
-  float* cout;  // GEMM outputs [CO_END]
-};
+// ---- scratch: one record per 64 points; a blob of F features = [hi: F/8 chunks][lo: F/8 chunks], chunk = 64 points x 16 B.
+// Four stage blocks per record, each the operand set of the GEMMs the dW kernel issues on it (chunk counts in brackets):
+//   stage 1 (S1)        : DZ2 [16]  XZ1 [16]
+//   stage 2 (F, S0)     : XZ2 [16]  DR [2]  DZ1 [16]  XG [4]
+//   stage 3 (C0, C1)    : DC1 [8]   XC [6]  XG' [4]   DC2 [8]  XC1 [8]
+//   stage 4 (C2, B0, B1): XC2 [8]   DR' [2] DH [8]    XE [4]   XH [8]  DOUT [4]
+// X tiles: XE encoding, XH h, XG [h0 slot | geo 30 | 1] (the pad position of the forward carries a constant 1: the weight rows of
+// that position are zero, and its column of the product is the bias gradient), XZ1 / XZ2 semantic hidden layers, XC [sh 16 | app 32],
+// XC1 / XC2 colour hidden layers; dY tiles: DH, DOUT (base), DZ1, DZ2 (semantic), DC1, DC2 (colour), DR = [d rgb_pre 3, 0, d logit, 0..].
+constexpr int kRecPoints = 64, kChunk = kRecPoints * 16;
+constexpr int blob_bytes(int chunks) { return 2 * chunks * kChunk; }
+constexpr int ST1 = 0, O_DZ2 = ST1, O_XZ1 = O_DZ2 + blob_bytes(16), ST1_BYTES = O_XZ1 + blob_bytes(16) - ST1;
+constexpr int ST2 = ST1 + ST1_BYTES, O_XZ2 = ST2, O_DR = O_XZ2 + blob_bytes(16), O_DZ1 = O_DR + blob_bytes(2), O_XG = O_DZ1 + blob_bytes(16),
+              ST2_BYTES = O_XG + blob_bytes(4) - ST2;
+constexpr int ST3 = ST2 + ST2_BYTES, O_DC1 = ST3, O_XC = O_DC1 + blob_bytes(8), O_XG2 = O_XC + blob_bytes(6), O_DC2 = O_XG2 + blob_bytes(4),
+              O_XC1 = O_DC2 + blob_bytes(8), ST3_BYTES = O_XC1 + blob_bytes(8) - ST3;
+constexpr int ST4 = ST3 + ST3_BYTES, O_XC2 = ST4, O_DR2 = O_XC2 + blob_bytes(8), O_DH = O_DR2 + blob_bytes(2), O_XE = O_DH + blob_bytes(8),
+              O_XH = O_XE + blob_bytes(4), O_DOUT = O_XH + blob_bytes(8), ST4_BYTES = O_DOUT + blob_bytes(4) - ST4;
+constexpr int kRecBytes = ST4 + ST4_BYTES;
+constexpr int kStageMax = ST2_BYTES;
+static_assert(ST1_BYTES <= kStageMax && ST3_BYTES <= kStageMax && ST4_BYTES <= kStageMax, "ring slot size");
+static_assert(kRecBytes % 128 == 0 && ST2 % 128 == 0 && ST3 % 128 == 0 && ST4 % 128 == 0, "bulk-copy alignment");
+constexpr int kFoldFloats = 256;  // v[128] = sum dlogit z2, s = sum dlogit (+ padding): reduced over CTAs, consumed by big_fold_kernel
 
 struct ChainArgs {
   KField F;
@@ -87,30 +96,38 @@ struct ChainArgs {
   const float* point_grads;
   const float* stash;
   const float* sample_rgb;
-  Bufs B;
-  int debug_flags;  // FNR_DEBUG_BWD (timing experiments only): bit 0 skip the table scatter, bit 2 skip the X / dY stores
+  uint8_t* records;  // scratch: ceil(N / 64) records of kRecBytes
+  float* fold;       // [kFoldFloats] zero-initialised: the chain adds s = sum dlogit at [128]
+  int debug_flags;   // FNR_DEBUG_BWD (timing experiments only): bit 0 skip the table scatter, bit 2 skip the X / dY stores
 };
 
-template <int K>
-__device__ __forceinline__ void st_a16(uint32_t ab, int k0, const float (&v)[16]) {
-  uint32_t h[8], l[8];
+// 16 values -> packed bf16 hi / lo words (two values per word)
+__device__ __forceinline__ void pack16(const float (&v)[16], uint32_t (&h)[8], uint32_t (&l)[8]) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) split_pack_bf16x2(v[2 * q], v[2 * q + 1], h[q], l[q]);
+}
+// K elements [k0, k0 + 16) of this thread's row -> A tile (depth K) in tensor memory
+template <int K>
+__device__ __forceinline__ void st_a16p(uint32_t ab, int k0, const uint32_t (&h)[8], const uint32_t (&l)[8]) {
   tmem_st8(ab + (k0 >> 1), h);
   tmem_st8(ab + K / 2 + (k0 >> 1), l);
 }
-
-// 256-bit stores (STG.E.ENL2.256): one whole 32-byte sector per lane and instruction; dst must be 32-byte aligned
-__device__ __forceinline__ void store8(float* dst, float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
-  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(a0), "f"(a1), "f"(a2), "f"(a3), "f"(a4), "f"(a5), "f"(a6),
-               "f"(a7)
-               : "memory");
+template <int K>
+__device__ __forceinline__ void st_a16(uint32_t ab, int k0, const float (&v)[16]) {
+  uint32_t h[8], l[8];
+  pack16(v, h, l);
+  st_a16p<K>(ab, k0, h, l);
 }
-__device__ __forceinline__ void store16(float* dst, const float (&v)[16]) {
-  store8(dst, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
-  store8(dst + 8, v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
+// features [k0, k0 + 16) of this thread's point -> blob (chunks = its feature count / 8) of the point's record; `rec` already
+// points at the record + (point % 64) * 16.  A warp writes 512 contiguous bytes per instruction.
+__device__ __forceinline__ void st_blob16(uint8_t* rec, int blob_off, int chunks, int k0, const uint32_t (&h)[8], const uint32_t (&l)[8]) {
+  uint8_t* p = rec + blob_off + (k0 >> 3) * kChunk;
+  *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(p + kChunk) = make_uint4(h[4], h[5], h[6], h[7]);
+  p += chunks * kChunk;
+  *reinterpret_cast<uint4*>(p) = make_uint4(l[0], l[1], l[2], l[3]);
+  *reinterpret_cast<uint4*>(p + kChunk) = make_uint4(l[4], l[5], l[6], l[7]);
 }
-__device__ __forceinline__ void store_one_col(float* dst) { store8(dst, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f); }
 
 // forward GEMM: A (TMEM, depth K) x W[N,K]^T
 template <int K, int N>
@@ -155,7 +172,6 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
   const KParams& P = a.P;
   const KParams& G = a.G;
   const KField& F = a.F;
-  const Bufs& B = a.B;
   float* sf = reinterpret_cast<float*>(smem + OFF_F32);
   float* stage = reinterpret_cast<float*>(smem + OFF_STAGE);
 
@@ -325,11 +341,14 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
   } else {
   // ================= compute warps =================
   reg_inc<216>();
+  // narrow bias gradients as per-thread running sums: half 0 -> d rgb_pre (col2 bias) and d logit (folded tail), both halves -> dout
+  float acc_dr[4] = {0.f, 0.f, 0.f, 0.f}, acc_dout[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) acc_dout[q] = 0.f;
 #pragma unroll 1
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const long long p = tile * 128 + row;
     const bool in_range = p < N;
-    const bool valid = in_range && !(a.debug_flags & 4);  // `valid` guards the scratch stores
     const long long pc = in_range ? p : N - 1;
     const int ray = (int)(pc / S);
     const float* o = a.Rr.origins + 3 * (size_t)ray;
@@ -341,6 +360,10 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
     const float d_sigma = __ldg(pg) * vm;
     const float d_logit = __ldg(pg + 4) * vm;
     const int cam = (F.appearance_mode == FNR_APP_PER_CAMERA) ? __ldg(a.Rr.camera_indices + ray) : 0;
+    // this point's row in its 64-point record (rows past N carry dY = 0, so whatever X they hold contributes nothing)
+    uint8_t* const rec = a.records + (size_t)(2 * tile + (row >> 6)) * kRecBytes + (row & 63) * 16;
+    const bool valid = !(a.debug_flags & 4);
+    uint32_t ph[8], pl[8];
 
     // ---- R1: encoding (stash) -> A0 ; X_enc ----
     {
@@ -351,11 +374,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
         const float4 u = __ldg(s4 + q);
         enc[4 * q] = u.x; enc[4 * q + 1] = u.y; enc[4 * q + 2] = u.z; enc[4 * q + 3] = u.w;
       }
-      st_a16<K_BASE0>(tr + R_A0, 16 * half, enc);
-      if (valid) {
-        store16(B.xe + (size_t)p * XW_E + 16 * half, enc);
-        if (half == 1) store_one_col(B.xe + (size_t)p * XW_E + 32);
-      }
+      pack16(enc, ph, pl);
+      st_a16p<K_BASE0>(tr + R_A0, 16 * half, ph, pl);
+      if (valid) st_blob16(rec, O_XE, 4, 16 * half, ph, pl);
     }
     FNR_ISSUE(issue_fwd<K_BASE0, N_BASE0>(tb + R_D0, tb + R_A0, wBase + OFF_W_BASE0))
 
@@ -373,15 +394,16 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
         v[q] = fmaxf(__uint_as_float(r[q]) + sf[B_BASE0 + 32 * half + 16 * j + q], 0.f);
         if (v[q] > 0.f) mask_h |= 1u << (16 * j + q);
       }
-      st_a16<K_BASE1>(tr + R_A1, 32 * half + 16 * j, v);
-      if (valid) store16(B.xh + (size_t)p * XW_H + 32 * half + 16 * j, v);
+      pack16(v, ph, pl);
+      st_a16p<K_BASE1>(tr + R_A1, 32 * half + 16 * j, ph, pl);
+      if (valid) st_blob16(rec, O_XH, 8, 32 * half + 16 * j, ph, pl);
     }
-    if (valid && half == 1) store_one_col(B.xh + (size_t)p * XW_H + 64);
     if (half == 0) {
       float sh[16];
       sh_degree4(__ldg(d), __ldg(d + 1), __ldg(d + 2), sh);
-      st_a16<K_COL0>(tr + R_A0, 0, sh);
-      if (valid) store16(B.xc + (size_t)p * XW_C, sh);
+      pack16(sh, ph, pl);
+      st_a16p<K_COL0>(tr + R_A0, 0, ph, pl);
+      if (valid) st_blob16(rec, O_XC, 6, 0, ph, pl);
     } else {
       const float* app = (F.appearance_mode == FNR_APP_PER_CAMERA) ? P.app_embedding + (size_t)cam * APP : nullptr;
 #pragma unroll
@@ -389,10 +411,10 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
         float v[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] = app ? __ldg(app + 16 * j + q) : 0.f;
-        st_a16<K_COL0>(tr + R_A0, SHD + 16 * j, v);
-        if (valid) store16(B.xc + (size_t)p * XW_C + SHD + 16 * j, v);
+        pack16(v, ph, pl);
+        st_a16p<K_COL0>(tr + R_A0, SHD + 16 * j, ph, pl);
+        if (valid) st_blob16(rec, O_XC, 6, SHD + 16 * j, ph, pl);
       }
-      if (valid) store_one_col(B.xc + (size_t)p * XW_C + K_COL0);
     }
     FNR_ISSUE(issue_fwd<K_BASE1, N_BASE1>(tb + R_D1, tb + R_A1, wBase + OFF_W_BASE1))
 
@@ -407,12 +429,16 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
 #pragma unroll
       for (int q = 0; q < 16; ++q) g[q] = __uint_as_float(r0[q]) + sf[B_BASE1 + 16 * half + q];
       if (half == 0) dsig_scale = sel ? expf(fminf(fmaxf(g[0], -15.f), 15.f)) : 0.f;  // trunc_exp backward
-      st_a16<K_SEM0>(tr + R_A1 + 64, 16 * half, g);
-      st_a16<K_COL0>(tr + R_A0, SHD + APP + 16 * half, g);
+      pack16(g, ph, pl);
+      st_a16p<K_SEM0>(tr + R_A1 + 64, 16 * half, ph, pl);
+      st_a16p<K_COL0>(tr + R_A0, SHD + APP + 16 * half, ph, pl);
       if (valid) {
-        store16(B.xg + (size_t)p * XW_G + 16 * half, g);
-        store16(B.xc + (size_t)p * XW_C + SHD + APP + 16 * half, g);
-        if (half == 1) store_one_col(B.xg + (size_t)p * XW_G + 32);
+        if (half == 1) {  // the stored copy carries a constant 1 in the pad position (bias-gradient column of S0 / C0)
+          g[15] = 1.0f;
+          pack16(g, ph, pl);
+        }
+        st_blob16(rec, O_XG, 4, 16 * half, ph, pl);
+        st_blob16(rec, O_XG2, 4, 16 * half, ph, pl);
       }
     }
     FNR_ISSUE(issue_fwd<K_SEM0, N_SEM0>(tb + R_D0, tb + R_A1 + 64, wBase + OFF_W_SEM0);
@@ -432,8 +458,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
         v[q] = fmaxf(__uint_as_float(r[q]) + sf[B_SEM0 + 64 * half + 16 * j + q], 0.f);
         if (v[q] > 0.f) mask_z1[j >> 1] |= 1u << (16 * (j & 1) + q);
       }
-      st_a16<K_SEM1>(tr + R_A1, 64 * half + 16 * j, v);
-      if (valid) store16(B.xz1 + (size_t)p * XW_Z + 64 * half + 16 * j, v);
+      pack16(v, ph, pl);
+      st_a16p<K_SEM1>(tr + R_A1, 64 * half + 16 * j, ph, pl);
+      if (valid) st_blob16(rec, O_XZ1, 16, 64 * half + 16 * j, ph, pl);
     }
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
@@ -446,12 +473,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
         v[q] = fmaxf(__uint_as_float(r[q]) + sf[B_COL0 + 32 * half + 16 * j + q], 0.f);
         if (v[q] > 0.f) mask_c1 |= 1u << (16 * j + q);
       }
-      st_a16<K_COL1>(tr + R_A0, 32 * half + 16 * j, v);
-      if (valid) store16(B.xc1 + (size_t)p * XW_C1 + 32 * half + 16 * j, v);
-    }
-    if (valid && half == 1) {
-      store_one_col(B.xz1 + (size_t)p * XW_Z + 128);
-      store_one_col(B.xc1 + (size_t)p * XW_C1 + 64);
+      pack16(v, ph, pl);
+      st_a16p<K_COL1>(tr + R_A0, 32 * half + 16 * j, ph, pl);
+      if (valid) st_blob16(rec, O_XC1, 8, 32 * half + 16 * j, ph, pl);
     }
     FNR_ISSUE(issue_fwd<K_SEM1, N_SEM1>(tb + R_D0, tb + R_A1, wBase + OFF_W_SEM1);
               issue_fwd<K_COL1, N_COL1>(tb + R_D1, tb + R_A0, wBase + OFF_W_COL1))
@@ -471,10 +495,12 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
         v[q] = fmaxf(__uint_as_float(r[q]) + sf[B_SEM1 + n], 0.f);
         dz[q] = v[q] > 0.f ? d_logit * sf[B_FOLD + n] : 0.f;
       }
-      st_a16<K_SEM1>(tr + R_A1, 64 * half + 16 * j, dz);
+      pack16(dz, ph, pl);
+      st_a16p<K_SEM1>(tr + R_A1, 64 * half + 16 * j, ph, pl);
       if (valid) {
-        store16(B.xz2 + (size_t)p * XW_Z + 64 * half + 16 * j, v);
-        store16(B.dz2 + (size_t)p * DW_Z + 64 * half + 16 * j, dz);
+        st_blob16(rec, O_DZ2, 16, 64 * half + 16 * j, ph, pl);
+        pack16(v, ph, pl);
+        st_blob16(rec, O_XZ2, 16, 64 * half + 16 * j, ph, pl);
       }
     }
 #pragma unroll
@@ -488,11 +514,10 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
         v[q] = fmaxf(__uint_as_float(r[q]) + sf[B_COL1 + 32 * half + 16 * j + q], 0.f);
         if (v[q] > 0.f) mask_c2 |= 1u << (16 * j + q);
       }
-      if (valid) store16(B.xc2 + (size_t)p * XW_C2 + 32 * half + 16 * j, v);
-    }
-    if (valid && half == 1) {
-      store_one_col(B.xz2 + (size_t)p * XW_Z + 128);
-      store_one_col(B.xc2 + (size_t)p * XW_C2 + 64);
+      if (valid) {
+        pack16(v, ph, pl);
+        st_blob16(rec, O_XC2, 8, 32 * half + 16 * j, ph, pl);
+      }
     }
     if (half == 0) {
       float dr[16];
@@ -504,7 +529,16 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
         dr[c] = __ldg(pg + 1 + c) * vm * rgb * (1.0f - rgb);  // sigmoid'
       }
       st_a16<16>(tr + R_A0, 0, dr);
-      if (valid) store8(B.dr + (size_t)p * DW_R, dr[0], dr[1], dr[2], 0.f, d_logit, 0.f, 0.f, 0.f);  // columns 4..7: dY of the folded tail
+      acc_dr[0] += dr[0];
+      acc_dr[1] += dr[1];
+      acc_dr[2] += dr[2];
+      acc_dr[3] += d_logit;
+      if (valid) {  // DR = [d rgb_pre 0..2, 0, d logit, 0 ...]: B operand of C2 (columns 0..2) and of the folded tail F (column 4)
+        dr[4] = d_logit;
+        pack16(dr, ph, pl);
+        st_blob16(rec, O_DR, 2, 0, ph, pl);
+        st_blob16(rec, O_DR2, 2, 0, ph, pl);
+      }
     }
     FNR_ISSUE(issue_dx<N_SEM1, K_SEM1>(tb + R_D0, tb + R_A1, wBase + OFF_W_SEM1);
               issue_dx<N_COL2, K_COL2>(tb + R_D1, tb + R_A0, wBase + OFF_W_COL2))
@@ -519,7 +553,10 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
       float v[16];
 #pragma unroll
       for (int q = 0; q < 16; ++q) v[q] = ((mask_z1[j >> 1] >> (16 * (j & 1) + q)) & 1u) ? __uint_as_float(r[q]) : 0.f;
-      if (valid) store16(B.dz1 + (size_t)p * DW_Z + 64 * half + 16 * j, v);
+      if (valid) {
+        pack16(v, ph, pl);
+        st_blob16(rec, O_DZ1, 16, 64 * half + 16 * j, ph, pl);
+      }
     }
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
@@ -529,8 +566,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
       float v[16];
 #pragma unroll
       for (int q = 0; q < 16; ++q) v[q] = ((mask_c2 >> (16 * j + q)) & 1u) ? __uint_as_float(r[q]) : 0.f;
-      st_a16<K_COL2>(tr + R_A0, 32 * half + 16 * j, v);
-      if (valid) store16(B.dc2 + (size_t)p * DW_C + 32 * half + 16 * j, v);
+      pack16(v, ph, pl);
+      st_a16p<K_COL2>(tr + R_A0, 32 * half + 16 * j, ph, pl);
+      if (valid) st_blob16(rec, O_DC2, 8, 32 * half + 16 * j, ph, pl);
     }
     FNR_ISSUE(issue_dx<N_COL1, K_COL1>(tb + R_D1 + 64, tb + R_A0, wBase + OFF_W_COL1))
 
@@ -544,8 +582,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
       float v[16];
 #pragma unroll
       for (int q = 0; q < 16; ++q) v[q] = ((mask_c1 >> (16 * j + q)) & 1u) ? __uint_as_float(r[q]) : 0.f;
-      st_a16<K_COL1>(tr + R_A0, 32 * half + 16 * j, v);
-      if (valid) store16(B.dc1 + (size_t)p * DW_C + 32 * half + 16 * j, v);
+      pack16(v, ph, pl);
+      st_a16p<K_COL1>(tr + R_A0, 32 * half + 16 * j, ph, pl);
+      if (valid) st_blob16(rec, O_DC1, 8, 32 * half + 16 * j, ph, pl);
     }
     FNR_ISSUE(issue_dx<N_COL0, K_COL0>(tb + R_D0, tb + R_A0, wBase + OFF_W_COL0))
 
@@ -589,8 +628,11 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
       for (int q = 0; q < 16; ++q) dout[q] = __uint_as_float(rg[q]);
       if (half == 0) dout[0] = d_sigma * dsig_scale;  // the h0 slot of the colour input carries no weight: its dX is 0
       else dout[15] = 0.f;                            // pad position
-      st_a16<N_BASE1>(tr + R_A1, 16 * half, dout);
-      if (valid) store16(B.dout + (size_t)p * DW_OUT + 16 * half, dout);
+      pack16(dout, ph, pl);
+      st_a16p<N_BASE1>(tr + R_A1, 16 * half, ph, pl);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc_dout[q] += dout[q];  // base1 bias gradient (its X tile h has no spare column)
+      if (valid) st_blob16(rec, O_DOUT, 4, 16 * half, ph, pl);
     }
     FNR_ISSUE(issue_dx<N_BASE1, K_BASE1>(tb + R_D1, tb + R_A1, wBase + OFF_W_BASE1))
 
@@ -604,8 +646,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
       float v[16];
 #pragma unroll
       for (int q = 0; q < 16; ++q) v[q] = ((mask_h >> (16 * j + q)) & 1u) ? __uint_as_float(r[q]) : 0.f;
-      st_a16<N_BASE0>(tr + R_A0, 32 * half + 16 * j, v);
-      if (valid) store16(B.dh + (size_t)p * DW_H + 32 * half + 16 * j, v);
+      pack16(v, ph, pl);
+      st_a16p<N_BASE0>(tr + R_A0, 32 * half + 16 * j, ph, pl);
+      if (valid) st_blob16(rec, O_DH, 8, 32 * half + 16 * j, ph, pl);
     }
     FNR_ISSUE(issue_dx<N_BASE0, K_BASE0>(tb + R_D0, tb + R_A0, wBase + OFF_W_BASE0))
 
@@ -625,6 +668,20 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
     named_bar_arrive(BAR_FULL, kCtaThreads);
     fence_before_sync();
   }
+  // flush the running sums: warp reduce, one atomic per warp and value
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const float sum = warp_sum_f(acc_dout[q]);
+    const int n = 16 * half + q;
+    if (lane == 0 && n < 1 + GEO && sum != 0.f) atomicAdd(G.base_b[1] + n, sum);
+  }
+  if (half == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float sum = warp_sum_f(acc_dr[c]);
+      if (lane == 0 && sum != 0.f) atomicAdd(c < 3 ? G.col_b[2] + c : a.fold + 128, sum);
+    }
+  }
   }  // compute warps
 #undef FNR_ISSUE
 #undef FNR_WAIT
@@ -634,136 +691,285 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
   if (warp == 0) tmem_dealloc(s_tmem_base, 512);
 }
 
-// GEMM products -> torch-layout gradient tensors (+=)
-__global__ void __launch_bounds__(256) big_unpack_kernel(const float* __restrict__ c, KParams P, KParams G) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
-  for (int i = t; i < 64 * XW_E; i += nt) {
-    const int n = i / XW_E, k = i % XW_E;
-    const float v = c[CO_B0 + i];
-    if (k < 32) G.base_w[0][n * ENC + k] += v;
-    else if (k == 32) G.base_b[0][n] += v;
-  }
-  for (int i = t; i < 32 * XW_H; i += nt) {
-    const int n = i / XW_H, k = i % XW_H;
-    if (n >= 1 + GEO) continue;
-    const float v = c[CO_B1 + i];
-    if (k < 64) G.base_w[1][n * H + k] += v;
-    else if (k == 64) G.base_b[1][n] += v;
-  }
-  for (int i = t; i < 128 * XW_G; i += nt) {
-    const int n = i / XW_G, k = i % XW_G;
-    const float v = c[CO_S0 + i];
-    if (k >= 1 && k <= GEO) G.sem_w[0][n * GEO + (k - 1)] += v;  // column 0 is the h0 slot
-    else if (k == 32) G.sem_b[0][n] += v;
-  }
-  for (int i = t; i < 128 * XW_Z; i += nt) {
-    const int n = i / XW_Z, k = i % XW_Z;
-    const float v = c[CO_S1 + i];
-    if (k < 128) G.sem_w[1][n * SW + k] += v;
-    else if (k == 128) G.sem_b[1][n] += v;
-  }
-  {  // folded tail: v[k] = sum dlogit z2[k], s = sum dlogit
-    const float* vv = c + CO_F;
-    const float s = vv[128];
-    for (int i = t; i < SOUT * SW; i += nt) {
-      const int j = i / SW, k = i % SW;
-      G.sem_w[2][i] += P.head_w[j] * vv[k];
-    }
-    for (int j = t; j < SOUT; j += nt) {
-      G.sem_b[2][j] += P.head_w[j] * s;
-      float acc = P.sem_b[2][j] * s;
-      for (int k = 0; k < SW; ++k) acc = fmaf(P.sem_w[2][j * SW + k], vv[k], acc);
-      G.head_w[j] += acc;
-    }
-    if (t == 0) G.head_b[0] += s;
-  }
-  for (int i = t; i < 64 * XW_C; i += nt) {
-    const int n = i / XW_C, k = i % XW_C;
-    const float v = c[CO_C0 + i];  // kernel K order [sh | app | h0-slot, geo, pad | 1] -> torch order [sh | geo | app]
-    if (k < SHD) G.col_w[0][n * CIN + k] += v;
-    else if (k < SHD + APP) G.col_w[0][n * CIN + SHD + GEO + (k - SHD)] += v;
-    else if (k >= SHD + APP + 1 && k <= SHD + APP + GEO) G.col_w[0][n * CIN + SHD + (k - SHD - APP - 1)] += v;
-    else if (k == K_COL0) G.col_b[0][n] += v;
-  }
-  for (int i = t; i < 64 * XW_C1; i += nt) {
-    const int n = i / XW_C1, k = i % XW_C1;
-    const float v = c[CO_C1 + i];
-    if (k < 64) G.col_w[1][n * H + k] += v;
-    else if (k == 64) G.col_b[1][n] += v;
-  }
-  for (int i = t; i < 3 * XW_C2; i += nt) {
-    const int n = i / XW_C2, k = i % XW_C2;
-    const float v = c[CO_C2 + i];
-    if (k < 64) G.col_w[2][n * H + k] += v;
-    else if (k == 64) G.col_b[2][n] += v;
-  }
-}
+// ======================================================================================================================
+// tc_big_dw_kernel: dW = dY^T X over all points, operands streamed by TMA, accumulators resident in tensor memory
+// ======================================================================================================================
+constexpr int kDwThreads = 256;   // warp 0: TMA producer, warp 1: MMA issue, all 8 warps: final flush
+constexpr int kDwSlots = 2;
+constexpr int DW_OFF_ONES = 0;                         // [2 chunks][64 points][16 B]: feature 0 = 1 (bias-gradient operand)
+constexpr int DW_OFF_RING = 2 * kChunk;
+constexpr int kDwSmem = DW_OFF_RING + kDwSlots * kStageMax + 1024;
+static_assert(kDwSmem <= 227 * 1024, "shared-memory budget");
+// accumulator columns (M = 128: lane = row; M = 64: row i in lane (i % 16) + 32 (i / 16))
+constexpr int A_S1 = 0;      // [dz2 128 x z1 128]
+constexpr int A_S1B = 128;   // [dz2 128 x 16]   column 0 = bias
+constexpr int A_F = 144;     // [z2 128 x 16]    column 4 = v
+constexpr int A_S0 = 160;    // [dz1 128 x 32]   columns 1..30 = geo, 31 = bias
+constexpr int A_C0A = 192;   // [dc1 64 x 48]    sh | app
+constexpr int A_C0B = 240;   // [dc1 64 x 32]    columns 1..30 = geo, 31 = bias
+constexpr int A_C1 = 272;    // [dc2 64 x 64]
+constexpr int A_C1B = 336;   // [dc2 64 x 16]    column 0 = bias
+constexpr int A_C2 = 352;    // [c2 64 x 16]     columns 0..2 = colour outputs
+constexpr int A_B0 = 368;    // [dh 64 x 32]
+constexpr int A_B0B = 400;   // [dh 64 x 16]     column 0 = bias
+constexpr int A_B1 = 416;    // [h 64 x 32]      columns 0..30 = base outputs
+static_assert(A_B1 + 32 <= 512, "tensor-memory budget");
 
-// ---- cuBLAS, resolved at first use (no link-time dependency: the C-ABI library must load without it) ----
-struct Cublas {
-  void* lib = nullptr;
-  cublasHandle_t handle = nullptr;
-  cublasStatus_t (*create)(cublasHandle_t*) = nullptr;
-  cublasStatus_t (*set_stream)(cublasHandle_t, cudaStream_t) = nullptr;
-  cublasStatus_t (*gemm_ex)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int, const void*, const void*, cudaDataType, int,
-                            const void*, cudaDataType, int, const void*, void*, cudaDataType, int, cublasComputeType_t, cublasGemmAlgo_t) = nullptr;
-  bool ok = false;
+struct DwArgs {
+  const uint8_t* records;
+  long long num_records;
+  KParams G;
+  float* fold;  // [kFoldFloats]: v[128] (+= over CTAs); [128] = s comes from the chain kernel
 };
 
-Cublas& cublas() {
-  static Cublas c;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    for (const char* name : {"libcublas.so.12", "libcublas.so", "/usr/local/cuda/lib64/libcublas.so.12"}) {
-      c.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
-      if (c.lib) break;
-    }
-    if (c.lib) {
-      c.create = reinterpret_cast<decltype(c.create)>(dlsym(c.lib, "cublasCreate_v2"));
-      c.set_stream = reinterpret_cast<decltype(c.set_stream)>(dlsym(c.lib, "cublasSetStream_v2"));
-      c.gemm_ex = reinterpret_cast<decltype(c.gemm_ex)>(dlsym(c.lib, "cublasGemmEx"));
-      if (c.create && c.set_stream && c.gemm_ex && c.create(&c.handle) == CUBLAS_STATUS_SUCCESS) c.ok = true;
-    }
-  }
-  return c;
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 
-// row-major C[n_out x xw] = dY[P x dw (lda)]^T X[P x xw]
-int gemm_dw(Cublas& cb, const float* dy, int ldd, int n_out, const float* x, int xw, long long Pn, float* cout) {
-  const float one = 1.f, zero = 0.f;
-  const cublasStatus_t s = cb.gemm_ex(cb.handle, CUBLAS_OP_N, CUBLAS_OP_T, xw, n_out, (int)Pn, &one, x, CUDA_R_32F, xw, dy, CUDA_R_32F, ldd, &zero,
-                                      cout, CUDA_R_32F, xw, CUBLAS_COMPUTE_32F_FAST_TF32, CUBLAS_GEMM_DEFAULT);
-  if (s != CUBLAS_STATUS_SUCCESS) {
-    set_error("cublasGemmEx failed with status %d", (int)s);
-    return FNR_ERR_CUDA;
+// ACC[M, NB] (+)= A[64 points, M]^T B[64 points, NB]: both tiles MN-major (chunk stride 1024 B), K = 64 points = 4 K-steps.
+// a / b: shared addresses of the hi blobs; a_lo / b_lo: byte offsets of the lo halves (0 = operand has no lo part).
+template <int M, int NB>
+__device__ __forceinline__ void issue_dw(uint32_t d_tmem, uint32_t a, uint32_t a_lo, uint32_t b, uint32_t b_lo, bool accumulate) {
+  constexpr uint32_t idesc = idesc_bf16_f32(M, NB) | (1u << 15) | (1u << 16);  // a_major = b_major = MN
+#pragma unroll
+  for (int ks = 0; ks < kRecPoints / 16; ++ks) {
+    const uint64_t ah = smem_desc(a + ks * 256, 128, kChunk);
+    const uint64_t bh = smem_desc(b + ks * 256, 128, kChunk);
+    mma_ss(d_tmem, ah, bh, idesc, accumulate || ks > 0);
+    if (a_lo) mma_ss(d_tmem, smem_desc(a + a_lo + ks * 256, 128, kChunk), bh, idesc, true);
+    if (b_lo) mma_ss(d_tmem, ah, smem_desc(b + b_lo + ks * 256, 128, kChunk), idesc, true);
   }
-  return FNR_OK;
+}
+
+__global__ void __launch_bounds__(kDwThreads, 1) tc_big_dw_kernel(const __grid_constant__ DwArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t s_full[kDwSlots], s_empty[kDwSlots], s_done;
+  __shared__ uint32_t s_tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const KParams& G = a.G;
+
+  if (warp == 0) tmem_alloc(&s_tmem_base, 512);
+  if (tid == 0) {
+    for (int i = 0; i < kDwSlots; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 1);
+    }
+    mbar_init(&s_done, 1);
+    mbar_fence_init();
+  }
+  for (int i = tid; i < 2 * kRecPoints; i += kDwThreads)  // ONES: chunk 0 = (1, 0, 0, ...) per point, chunk 1 = 0
+    *reinterpret_cast<uint4*>(smem + DW_OFF_ONES + i * 16) = make_uint4(i < kRecPoints ? 0x00003F80u : 0u, 0u, 0u, 0u);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+
+  const uint32_t tb = s_tmem_base;
+  const uint32_t sb = smem_u32(smem);
+  const long long my_records = a.num_records > blockIdx.x ? (a.num_records - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  constexpr int kStageOff[4] = {ST1, ST2, ST3, ST4};
+  constexpr int kStageBytes[4] = {ST1_BYTES, ST2_BYTES, ST3_BYTES, ST4_BYTES};
+
+  if (warp == 0) {
+    // ---- TMA producer: one bulk copy per stage block into the ring
+    if (elect_one_sync()) {
+      long long it = 0;
+      for (long long i = 0; i < my_records; ++i) {
+        const uint8_t* rec = a.records + (size_t)(blockIdx.x + i * gridDim.x) * kRecBytes;
+#pragma unroll
+        for (int st = 0; st < 4; ++st, ++it) {
+          const int slot = (int)(it % kDwSlots);
+          const uint32_t use = (uint32_t)(it / kDwSlots);
+          mbar_wait(&s_empty[slot], (use & 1u) ^ 1u);  // the MMAs that read this slot's previous contents have completed
+          const uint32_t bar = smem_u32(&s_full[slot]);
+          mbar_expect_tx(bar, (uint32_t)kStageBytes[st]);
+          bulk_g2s(sb + DW_OFF_RING + slot * kStageMax, rec + kStageOff[st], (uint32_t)kStageBytes[st], bar);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---- MMA issue: every stage block is the operand set of the GEMMs issued on it
+    if (elect_one_sync()) {
+      long long it = 0;
+      const uint32_t ones = sb + DW_OFF_ONES;
+      for (long long i = 0; i < my_records; ++i) {
+        const bool acc = i > 0;
+#pragma unroll
+        for (int st = 0; st < 4; ++st, ++it) {
+          const int slot = (int)(it % kDwSlots);
+          const uint32_t use = (uint32_t)(it / kDwSlots);
+          mbar_wait(&s_full[slot], use & 1u);
+          fence_after_sync();
+          const uint32_t base = sb + DW_OFF_RING + slot * kStageMax - kStageOff[st];  // record-relative offsets below
+          if (st == 0) {
+            issue_dw<128, 128>(tb + A_S1, base + O_DZ2, 16 * kChunk, base + O_XZ1, 16 * kChunk, acc);
+            issue_dw<128, 16>(tb + A_S1B, base + O_DZ2, 16 * kChunk, ones, 0, acc);
+          } else if (st == 1) {
+            issue_dw<128, 16>(tb + A_F, base + O_XZ2, 16 * kChunk, base + O_DR, 2 * kChunk, acc);
+            issue_dw<128, 32>(tb + A_S0, base + O_DZ1, 16 * kChunk, base + O_XG, 4 * kChunk, acc);
+          } else if (st == 2) {
+            issue_dw<64, 48>(tb + A_C0A, base + O_DC1, 8 * kChunk, base + O_XC, 6 * kChunk, acc);
+            issue_dw<64, 32>(tb + A_C0B, base + O_DC1, 8 * kChunk, base + O_XG2, 4 * kChunk, acc);
+            issue_dw<64, 64>(tb + A_C1, base + O_DC2, 8 * kChunk, base + O_XC1, 8 * kChunk, acc);
+            issue_dw<64, 16>(tb + A_C1B, base + O_DC2, 8 * kChunk, ones, 0, acc);
+          } else {
+            issue_dw<64, 16>(tb + A_C2, base + O_XC2, 8 * kChunk, base + O_DR2, 2 * kChunk, acc);
+            issue_dw<64, 32>(tb + A_B0, base + O_DH, 8 * kChunk, base + O_XE, 4 * kChunk, acc);
+            issue_dw<64, 16>(tb + A_B0B, base + O_DH, 8 * kChunk, ones, 0, acc);
+            issue_dw<64, 32>(tb + A_B1, base + O_XH, 8 * kChunk, base + O_DOUT, 4 * kChunk, acc);
+          }
+          mma_commit(&s_empty[slot]);  // arrives when the MMAs above have finished reading the slot
+        }
+      }
+      mma_commit(&s_done);
+    }
+    __syncwarp();
+  }
+
+  // ---- flush: every accumulator once per CTA, atomics into the torch-layout gradient tensors
+  if (my_records > 0) {
+    mbar_wait(&s_done, 0);
+    fence_after_sync();
+    const int quarter = warp & 3, half = warp >> 2;  // 8 warps: lane quarter x column half
+    const uint32_t tr = tb + ((uint32_t)(quarter * 32) << 16);
+    const int row128 = quarter * 32 + lane;            // M = 128 accumulators: row = lane
+    const bool own64 = lane < 16;                      // M = 64 accumulators: rows live in lanes 0..15 of every quarter
+    const int row64 = 16 * quarter + lane;
+    uint32_t r[16];
+    // S1: d W_sem1[n][k], n = row, k = column
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const int c0 = 64 * half + 16 * j;
+      tmem_ld16(tr + A_S1 + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 16; ++q) atomicAdd(G.sem_w[1] + row128 * SW + c0 + q, __uint_as_float(r[q]));
+    }
+    tmem_ld16(tr + (half == 0 ? A_S1B : A_F), r);
+    tmem_ld_wait();
+    if (half == 0) atomicAdd(G.sem_b[1] + row128, __uint_as_float(r[0]));
+    else atomicAdd(a.fold + row128, __uint_as_float(r[4]));  // v[k] = sum dlogit z2[k]
+    // S0: d W_sem0[n][geo], bias in column 31
+    tmem_ld16(tr + A_S0 + 16 * half, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int kk = 16 * half + q;
+      if (kk >= 1 && kk <= GEO) atomicAdd(G.sem_w[0] + row128 * GEO + (kk - 1), __uint_as_float(r[q]));
+      else if (kk == 31) atomicAdd(G.sem_b[0] + row128, __uint_as_float(r[q]));
+    }
+    // M = 64 accumulators
+    float* gw0 = G.col_w[0] + row64 * CIN;
+#pragma unroll 1
+    for (int j = half; j < 3; j += 2) {  // C0A: 48 columns [sh 16 | app 32] -> torch order [sh | geo | app]
+      tmem_ld16(tr + A_C0A + 16 * j, r);
+      tmem_ld_wait();
+      if (own64) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int k = 16 * j + q;
+          atomicAdd(gw0 + (k < SHD ? k : SHD + GEO + (k - SHD)), __uint_as_float(r[q]));
+        }
+      }
+    }
+    tmem_ld16(tr + A_C0B + 16 * half, r);
+    tmem_ld_wait();
+    if (own64) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int kk = 16 * half + q;
+        if (kk >= 1 && kk <= GEO) atomicAdd(gw0 + SHD + (kk - 1), __uint_as_float(r[q]));
+        else if (kk == 31) atomicAdd(G.col_b[0] + row64, __uint_as_float(r[q]));
+      }
+    }
+#pragma unroll 1
+    for (int j = 0; j < 2; ++j) {  // C1
+      const int c0 = 32 * half + 16 * j;
+      tmem_ld16(tr + A_C1 + c0, r);
+      tmem_ld_wait();
+      if (own64) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) atomicAdd(G.col_w[1] + row64 * H + c0 + q, __uint_as_float(r[q]));
+      }
+    }
+    tmem_ld16(tr + (half == 0 ? A_C1B : A_C2), r);
+    tmem_ld_wait();
+    if (own64) {
+      if (half == 0) atomicAdd(G.col_b[1] + row64, __uint_as_float(r[0]));
+      else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) atomicAdd(G.col_w[2] + c * H + row64, __uint_as_float(r[c]));  // rows = c2 features
+      }
+    }
+    tmem_ld16(tr + A_B0 + 16 * half, r);
+    tmem_ld_wait();
+    if (own64) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) atomicAdd(G.base_w[0] + row64 * ENC + 16 * half + q, __uint_as_float(r[q]));
+    }
+    tmem_ld16(tr + (half == 0 ? A_B0B : A_B1), r);
+    tmem_ld_wait();
+    if (own64) {
+      if (half == 0) atomicAdd(G.base_b[0] + row64, __uint_as_float(r[0]));
+      else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) atomicAdd(G.base_w[1] + q * H + row64, __uint_as_float(r[q]));  // rows = h features, columns = outputs 0..15
+      }
+    }
+    if (half == 1) {
+      tmem_ld16(tr + A_B1 + 16, r);
+      tmem_ld_wait();
+      if (own64) {
+#pragma unroll
+        for (int q = 0; q < 15; ++q) atomicAdd(G.base_w[1] + (16 + q) * H + row64, __uint_as_float(r[q]));  // outputs 16..30 (31 is the pad)
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(s_tmem_base, 512);
+}
+
+// folded semantic tail from v[k] = sum dlogit z2[k] and s = sum dlogit:
+//   logit = head_w . (W_sem2 z2 + b_sem2) + head_b
+__global__ void __launch_bounds__(256) big_fold_kernel(const float* __restrict__ fold, KParams P, KParams G) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  const float* vv = fold;
+  const float s = fold[128];
+  for (int i = t; i < SOUT * SW; i += nt) {
+    const int j = i / SW, k = i % SW;
+    G.sem_w[2][i] += P.head_w[j] * vv[k];
+  }
+  for (int j = t; j < SOUT; j += nt) {
+    G.sem_b[2][j] += P.head_w[j] * s;
+    float acc = P.sem_b[2][j] * s;
+    for (int k = 0; k < SW; ++k) acc = fmaf(P.sem_w[2][j * SW + k], vv[k], acc);
+    G.head_w[j] += acc;
+  }
+  if (t == 0) G.head_b[0] += s;
 }
 
 }  // namespace
 
 size_t tc_big_backward_scratch_bytes(long long num_points) {
-  return (size_t)num_points * kFloatsPerPoint * sizeof(float) + (size_t)CO_END * sizeof(float) + 4096;
+  const long long records = 2 * ((num_points + 127) / 128);
+  return (size_t)records * kRecBytes + (size_t)kFoldFloats * sizeof(float) + 4096;
 }
 
 bool tc_big_backward_supported(const KField& F, const KFieldBwd& B) {
   return B.stash_encoding != nullptr && B.sample_rgb != nullptr && B.extra != nullptr && !F.pass_semantic_gradients &&
-         (F.appearance_mode == FNR_APP_PER_CAMERA || F.appearance_mode == FNR_APP_ZEROS) && cublas().ok;
+         (F.appearance_mode == FNR_APP_PER_CAMERA || F.appearance_mode == FNR_APP_ZEROS);
 }
 
 int launch_tc_big_field_backward(const KField& F, const KParams& P, const KParams& G, const KRays& Rr, const KFieldBwd& Bw, cudaStream_t st) {
   const long long N = (long long)Rr.R * Rr.S;
   if (N == 0) return FNR_OK;
-  if (N > 0x7fffffffLL) {
-    set_error("too many points for the cuBLAS reduction dimension");
-    return FNR_ERR_UNSUPPORTED;
-  }
-  Cublas& cb = cublas();
-  if (!cb.ok) {
-    set_error("cuBLAS is not available (dlopen libcublas.so.12)");
-    return FNR_ERR_UNSUPPORTED;
-  }
   if (Bw.extra_bytes < tc_big_backward_scratch_bytes(N)) {
     set_error("scratch too small for the big-family tensor-core backward");
     return FNR_ERR_INVALID_ARGUMENT;
@@ -772,6 +978,8 @@ int launch_tc_big_field_backward(const KField& F, const KParams& P, const KParam
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_big_backward_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tc_big_backward_chain_kernel)");
+    e = cudaFuncSetAttribute(tc_big_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmem);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tc_big_dw_kernel)");
     configured = true;
   }
   ChainArgs a;
@@ -786,37 +994,26 @@ int launch_tc_big_field_backward(const KField& F, const KParams& P, const KParam
   a.point_grads = Bw.point_grads;
   a.stash = Bw.stash_encoding;
   a.sample_rgb = Bw.sample_rgb;
-  float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(Bw.extra) + 255) & ~(uintptr_t)255);
-  auto take = [&](int width) {
-    float* ptr = base;
-    base += (size_t)N * width;
-    return ptr;
-  };
-  Bufs& B = a.B;
-  B.xe = take(XW_E); B.xh = take(XW_H); B.xg = take(XW_G); B.xz1 = take(XW_Z); B.xz2 = take(XW_Z); B.xc = take(XW_C); B.xc1 = take(XW_C1);
-  B.xc2 = take(XW_C2); B.dh = take(DW_H); B.dout = take(DW_OUT); B.dz1 = take(DW_Z); B.dz2 = take(DW_Z); B.dc1 = take(DW_C); B.dc2 = take(DW_C);
-  B.dr = take(DW_R);
-  B.cout = base;
   const long long tiles = (N + 127) / 128;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(Bw.extra) + 255) & ~(uintptr_t)255);
+  a.fold = reinterpret_cast<float*>(base);
+  a.records = base + 1024;
+  if (int rc = check_cuda(cudaMemsetAsync(a.fold, 0, kFoldFloats * sizeof(float), st), "cudaMemsetAsync(fold)")) return rc;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   tc_big_backward_chain_kernel<<<grid, kCtaThreads, kSmemBytes, st>>>(a);
-  if (int rc = check_cuda(cudaGetLastError(), "tc_big_backward_chain_kernel")) return rc;
+  if (int rc = check_launch("tc_big_backward_chain_kernel")) return rc;
+  if (a.debug_flags & 4) return FNR_OK;  // timing experiment: no X / dY tiles were written
 
-  if (cb.set_stream(cb.handle, st) != CUBLAS_STATUS_SUCCESS) {
-    set_error("cublasSetStream failed");
-    return FNR_ERR_CUDA;
-  }
-  int rc;
-  if ((rc = gemm_dw(cb, B.dh, DW_H, 64, B.xe, XW_E, N, B.cout + CO_B0))) return rc;
-  if ((rc = gemm_dw(cb, B.dout, DW_OUT, 32, B.xh, XW_H, N, B.cout + CO_B1))) return rc;
-  if ((rc = gemm_dw(cb, B.dz1, DW_Z, 128, B.xg, XW_G, N, B.cout + CO_S0))) return rc;
-  if ((rc = gemm_dw(cb, B.dz2, DW_Z, 128, B.xz1, XW_Z, N, B.cout + CO_S1))) return rc;
-  if ((rc = gemm_dw(cb, B.dr + 4, DW_R, 4, B.xz2, XW_Z, N, B.cout + CO_F))) return rc;  // dY = [d logit, 0, 0, 0]: row 0 = v | s
-  if ((rc = gemm_dw(cb, B.dc1, DW_C, 64, B.xc, XW_C, N, B.cout + CO_C0))) return rc;
-  if ((rc = gemm_dw(cb, B.dc2, DW_C, 64, B.xc1, XW_C1, N, B.cout + CO_C1))) return rc;
-  if ((rc = gemm_dw(cb, B.dr, DW_R, 4, B.xc2, XW_C2, N, B.cout + CO_C2))) return rc;
-  big_unpack_kernel<<<64, 256, 0, st>>>(B.cout, P, G);
-  return check_cuda(cudaGetLastError(), "big_unpack_kernel");
+  DwArgs d;
+  d.records = a.records;
+  d.num_records = 2 * tiles;
+  d.G = G;
+  d.fold = a.fold;
+  const int dgrid = (int)(d.num_records < sm_count() ? d.num_records : sm_count());
+  tc_big_dw_kernel<<<dgrid, kDwThreads, kDwSmem, st>>>(d);
+  if (int rc = check_launch("tc_big_dw_kernel")) return rc;
+  big_fold_kernel<<<32, 256, 0, st>>>(a.fold, P, G);
+  return check_launch("big_fold_kernel");
 }
 
 }  // namespace fnr

@@ -772,7 +772,7 @@ int launch_tc_field_backward(Family fam, const KField& F, const KParams& P, cons
   const long long tiles = (N + 127) / 128;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   tc_field_backward_kernel<<<grid, kT, kSmem, st>>>(a);
-  return check_cuda(cudaGetLastError(), "tc_field_backward_kernel");
+  return check_launch("tc_field_backward_kernel");
 }
 
 }  // namespace fnr

@@ -37,13 +37,18 @@ namespace {
 constexpr int kSlots = 2;
 constexpr int kSlotThreads = 256;
 constexpr int kChainThreads = kSlots * kSlotThreads;  // warps 0..15
-constexpr int kGatherWarps = 8;
-constexpr int kGatherThreads = kGatherWarps * 32;     // warps 16..23
+#ifndef FNR_WS_GATHER_WARPS
+#define FNR_WS_GATHER_WARPS 16
+#endif
+constexpr int kGatherWarps = FNR_WS_GATHER_WARPS;     // 8: thread pair per point (8 levels each); 16: four threads per point (4 levels each)
+constexpr int kGatherThreads = kGatherWarps * 32;     // warps 16..
+constexpr int kLv = 16 / (kGatherWarps / 4);          // hash levels per gather thread
+constexpr int kCoarseLevels = 8;                      // levels 0..7 are loaded directly (coalescing), 8..15 staged with cp.async
 constexpr int kCtaThreads = kChainThreads + kGatherThreads;
 constexpr int kMaxGroupPoints = 768;
 constexpr int kEnc = 3;    // encoding buffers in tensor memory
 #ifndef FNR_WS_DEPTH
-#define FNR_WS_DEPTH 4
+#define FNR_WS_DEPTH 2
 #endif
 constexpr int kDepth = FNR_WS_DEPTH;  // (tile, level) items in flight per gather thread
 
@@ -71,19 +76,22 @@ constexpr int OFF_SEL = OFF_SAMPLES + kMaxGroupPoints * 5 * 4;      // [kEnc][12
 // gather stage of one warp and one item: 4 x [lane] 16 B pair rows | 4 x [lane] 8 B single rows | [lane] 16 B (ox, oy, oz, flags)
 constexpr int STAGE_PAIR = 0, STAGE_SINGLE = 4 * 512, STAGE_META = STAGE_SINGLE + 4 * 256, STAGE_BYTES = STAGE_META + 512;
 constexpr int OFF_STAGE = (OFF_SEL + kEnc * 128 + 127) & ~127;
-constexpr int OFF_END = OFF_STAGE + kGatherWarps * kDepth * STAGE_BYTES;
+constexpr int kFineWarps = kGatherWarps / 2;  // the gather warps of levels 8..15 stage their rows with cp.async; the others load directly
+constexpr int OFF_END = OFF_STAGE + kFineWarps * kDepth * STAGE_BYTES;
 constexpr int kSmemBytes = OFF_END + 1024;
 static_assert(kSmemBytes <= 227 * 1024, "shared-memory budget");
 static_assert(OFF_BIAS % 16 == 0 && OFF_SAMPLES % 16 == 0 && STAGE_BYTES % 128 == 0, "alignment");
-static_assert(kDepth >= 1 && kDepth <= 8, "pipeline depth");
+static_assert(kDepth >= 1 && kDepth <= kLv, "pipeline depth");
+static_assert(kGatherWarps == 8 || kGatherWarps == 16, "gather warps");
 
 constexpr int C_X = 0, C_Y = 64, C_C = 80, C_Z = 144, kSlotCols = 208, C_ENC = kSlots * kSlotCols;
 static_assert(C_ENC + kEnc * 32 <= 512, "tensor-memory budget");
 
 constexpr int BAR_SLOT0 = 1, BAR_CHAIN = 3;
 // register split (setmaxnreg): 768 threads are launched with 80 registers; the gather warps hand 16 each to the chain warps
-constexpr int kGatherRegs = 64, kChainRegs = 88;
-static_assert(kGatherThreads * kGatherRegs + kChainThreads * kChainRegs <= kCtaThreads * 80, "register pool");
+constexpr int kLaunchRegs = kCtaThreads == 1024 ? 64 : 80;
+constexpr int kGatherRegs = kCtaThreads == 1024 ? 56 : 64, kChainRegs = kCtaThreads == 1024 ? 72 : 88;
+static_assert(kGatherThreads * kGatherRegs + kChainThreads * kChainRegs <= kCtaThreads * kLaunchRegs, "register pool");
 
 struct WsArgs {
   KField F;
@@ -93,7 +101,8 @@ struct WsArgs {
   KComposite Cm;
   int rays_per_group;
   int composite;
-  int debug;  // FNR_DEBUG_FWD: block 0 prints where each role waited (timing experiments only)
+  int debug;  // FNR_DEBUG_FWD (timing experiments only; results are wrong with bits 2..8 set): bit 1 block 0 prints where each role
+              // waited, 2 fine warps skip their table copies, 4 coarse warps skip their table loads, 8 chain slots skip the MLPs
   KExport E;
 };
 
@@ -105,12 +114,27 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+
 // K elements [16 s, 16 s + 16) of this thread's row -> operand region `reg` (lane-adjusted address): [hi 8 | lo 8] columns
 __device__ __forceinline__ void st_kstep(uint32_t reg, int s, const float (&v)[16]) {
   uint32_t w[16];
 #pragma unroll
   for (int q = 0; q < 8; ++q) split_pack_bf16x2(v[2 * q], v[2 * q + 1], w[q], w[8 + q]);
   tmem_st16(reg + 16 * s, w);
+}
+
+// a gather thread's share of the encoding operand (K = 32, two k-steps): 8 levels = k-step lq; 4 levels = half of k-step lq / 2
+__device__ __forceinline__ void st_encoding(uint32_t reg, int lq, const float (&v)[16]) { st_kstep(reg, lq, v); }
+__device__ __forceinline__ void st_encoding(uint32_t reg, int lq, const float (&v)[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) split_pack_bf16x2(v[2 * q], v[2 * q + 1], h[q], l[q]);
+  const uint32_t col = reg + 16 * (lq >> 1) + 4 * (lq & 1);  // K elements 8 lq .. 8 lq + 7 -> 4 hi + 4 lo columns
+  tmem_st4(col, h);
+  tmem_st4(col + 8, l);
 }
 
 // in-place epilogue of accumulator columns [16 s, 16 s + 16): v = f(column, x) replaces them as operand k-step s
@@ -140,14 +164,30 @@ __device__ __forceinline__ void issue_gemm_tsi(uint32_t d_tmem, uint32_t a_tmem,
   }
 }
 
+// waits that are expected to be long (another role has to produce a tile): back off so that the spin does not take issue slots
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+#ifdef FNR_WS_CG
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+#else
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+// predicated form (no divergent branch around the copy)
+__device__ __forceinline__ void cp_async8_if(bool pred, uint32_t dst, const void* src) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %2, 0;\n\t"
+      "@p cp.async.ca.shared.global [%0], [%1], 8;\n\t}" ::"r"(dst), "l"(src), "r"((uint32_t)pred)
+      : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -190,7 +230,8 @@ __device__ __forceinline__ TilePoint tile_point(const WsArgs& a, int ray0, int p
   return t;
 }
 
-template <bool kExport>
+// kDbg: the FNR_DEBUG_FWD instantiation (role timers, experiment switches); the production instantiation carries none of it
+template <bool kExport, bool kDbg>
 __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_ws_kernel(const __grid_constant__ WsArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -266,132 +307,189 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_ws_kernel(co
   const int quarter = warp & 3;
   const int row = quarter * 32 + lane;  // TMEM lane = point of the tile (warp w may touch lanes 32 (w % 4) ..)
   const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-  const bool prof = a.debug && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 8 || warp == 16);
-  long long t_wait_a = 0, t_wait_b = 0, t_total = 0;
+  const bool prof = kDbg && (a.debug & 1) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 8 || warp == 16 || warp == 16 + kGatherWarps / 2);
+  long long t_wait_a = 0, t_wait_b = 0, t_wait_c = 0, t_wait_d = 0, t_total = 0;
   if (prof) t_total = clock64();
 
   if (warp >= kChainThreads / 32) {
     // ========================= gather warps =========================
     reg_dec<kGatherRegs>();
     const int gw = warp - kChainThreads / 32;
-    const int hf = gw >> 2;  // levels 8 hf .. 8 hf + 7 -> encoding k-step hf
+    const int lq = gw >> 2;          // this warp's levels: kLv lq .. kLv lq + kLv - 1
+    const int l0 = kLv * lq;
+    const bool coarse = l0 < kCoarseLevels;
     const float2* __restrict__ table = reinterpret_cast<const float2*>(P.hash_table);
     const uint32_t hmask = (1u << F.log2T) - 1u;
-    const uint32_t stage0 = smem_u32(smem + OFF_STAGE) + (uint32_t)(gw * kDepth) * STAGE_BYTES;
+    const uint32_t stage0 = smem_u32(smem + OFF_STAGE) + (uint32_t)((gw - 4 * (kCoarseLevels / kLv)) * kDepth) * STAGE_BYTES;  // fine warps only
     const uint32_t enc0 = tmem0 + lane_off + C_ENC;
 
-    float enc[16];
-    int issued = 0;       // items issued so far (stage = issued % kDepth)
-    int seq = 0;          // tile sequence number of the tile being issued
-    TilePoint prev{};     // the tile whose last levels are still in flight
-    int prev_seq = -1;
+    float enc[2 * kLv];
+    int seq = 0;          // tile sequence number of the tile being gathered
 
-    auto issue_item = [&](const TilePoint& tp, int li) {
-      const int l = 8 * hf + li;
-      const LevelCell c = level_cell(tp.pos, F.scalings[l]);
-      const uint32_t base = (uint32_t)l << F.log2T;
-      // x-neighbours (floor x even, ceil = floor + 1) are adjacent table rows r, r^1: one 16-byte copy fetches both;
-      // only lanes with an odd floor x copy the ceil-x row separately.  Corner pairs (x floor, x ceil) per (y,z):
-      // (6,5) (7,4) (2,1) (3,0).
-      const bool pair = ((c.hx[0] & 1u) == 0u) && (c.hx[1] == c.hx[0] + 1u);
-      constexpr int kf[4] = {6, 7, 2, 3}, kc[4] = {5, 4, 1, 0};
-      const uint32_t st = stage0 + (uint32_t)(issued % kDepth) * STAGE_BYTES;
-      uint32_t flags = pair ? 1u : 0u;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t rf = corner_row(c, kf[q], hmask, base);
-        flags |= (rf & 1u) << (1 + q);
-        cp_async16(st + STAGE_PAIR + q * 512 + lane * 16, table + (rf & ~1u));
-        if (!pair) cp_async8(st + STAGE_SINGLE + q * 256 + lane * 8, table + corner_row(c, kc[q], hmask, base));
-      }
-      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + STAGE_META + lane * 16), "f"(c.ox), "f"(c.oy), "f"(c.oz),
-                   "f"(__uint_as_float(flags))
-                   : "memory");
-      cp_async_commit();
-      ++issued;
-    };
-    // blend the item issued kDepth items ago (stage = issued % kDepth, the one the next issue overwrites) -> enc[2 li ..]
-    auto blend_item = [&](int li) {
-      const uint32_t st = stage0 + (uint32_t)(issued % kDepth) * STAGE_BYTES;
-      float ox, oy, oz, fl;
-      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(ox), "=f"(oy), "=f"(oz), "=f"(fl) : "r"(st + STAGE_META + lane * 16) : "memory");
-      const uint32_t flags = __float_as_uint(fl);
-      const bool pair = flags & 1u;
-      constexpr int kf[4] = {6, 7, 2, 3}, kc[4] = {5, 4, 1, 0};
-      float2 f[8];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float4 pv;
-        float2 sv;
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(pv.x), "=f"(pv.y), "=f"(pv.z), "=f"(pv.w) : "r"(st + STAGE_PAIR + q * 512 + lane * 16) : "memory");
-        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(sv.x), "=f"(sv.y) : "r"(st + STAGE_SINGLE + q * 256 + lane * 8) : "memory");
-        const bool f_first = ((flags >> (1 + q)) & 1u) == 0u;
-        f[kf[q]] = f_first ? make_float2(pv.x, pv.y) : make_float2(pv.z, pv.w);
-        const float2 nb = f_first ? make_float2(pv.z, pv.w) : make_float2(pv.x, pv.y);
-        f[kc[q]] = pair ? nb : sv;
-      }
-      LevelCell c;
-      c.ox = ox;
-      c.oy = oy;
-      c.oz = oz;
-      const float2 r = trilerp(f, c);
-      enc[2 * li] = r.x;
-      enc[2 * li + 1] = r.y;
-    };
-    // a finished tile: stash (backward), encoding operand into the ring buffer, selector bytes, signal the chain slot
+    // a finished tile: stash (backward), this thread's K elements [2 l0, 2 l0 + 2 kLv) of the encoding operand into the ring
+    // buffer, selector bytes, signal the chain slot
     auto finish_tile = [&](const TilePoint& tp, int tseq) {
       if (!kExport && a.O.stash_encoding && tp.valid) {
-        float* stp = a.O.stash_encoding + tp.gp * ENC + 16 * hf;  // 64-byte aligned: two whole sectors per thread
-        st_global_v8(stp, enc[0], enc[1], enc[2], enc[3], enc[4], enc[5], enc[6], enc[7]);
-        st_global_v8(stp + 8, enc[8], enc[9], enc[10], enc[11], enc[12], enc[13], enc[14], enc[15]);
+        float* stp = a.O.stash_encoding + tp.gp * ENC + 2 * l0;  // 32-byte aligned: whole sectors per thread
+#pragma unroll
+        for (int j = 0; j < kLv / 4; ++j)
+          st_global_v8(stp + 8 * j, enc[8 * j], enc[8 * j + 1], enc[8 * j + 2], enc[8 * j + 3], enc[8 * j + 4], enc[8 * j + 5], enc[8 * j + 6], enc[8 * j + 7]);
       }
       const int e = tseq % kEnc, use = tseq / kEnc;
       long long t0 = 0;
       if (prof) t0 = clock64();
-      mbar_wait(&s_empty[e], (uint32_t)((use & 1) ^ 1));  // the base0 GEMM of this buffer's previous tile has completed
+      mbar_wait_sleep(&s_empty[e], (uint32_t)((use & 1) ^ 1));  // the base0 GEMM of this buffer's previous tile has completed
       if (prof) t_wait_a += clock64() - t0;
       fence_after_sync();
-      st_kstep(enc0 + 32 * e, hf, enc);
-      if (hf == 0) s_sel[e * 128 + row] = tp.sel ? 1 : 0;
+      st_encoding(enc0 + 32 * e, lq, enc);
+      if (lq == 0) s_sel[e * 128 + row] = tp.sel ? 1 : 0;
       tmem_st_wait();
       fence_before_sync();
       mbar_arrive(&s_full[e]);
     };
 
-    for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
-      const int ray0 = group * G;
-      const int pts = min(G, R - ray0) * S;
-      const int tiles = (pts + 127) / 128;
+    if (coarse) {
+      // ---- coarse levels: the 32 lanes of a warp are consecutive samples of a ray and share grid cells (a warp spans 1.3 cells at
+      // level 0, 12 at level 7 on the bench batch), so a direct load coalesces to a few sectors per instruction while a cp.async
+      // costs one L1TEX pass per LANE.  Loads go through registers.
+      for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
+        const int ray0 = group * G;
+        const int pts = min(G, R - ray0) * S;
+        const int tiles = (pts + 127) / 128;
 #pragma unroll 1
-      for (int tile = 0; tile < tiles; ++tile, ++seq) {
-        const TilePoint cur = tile_point<kExport>(a, ray0, pts, S, tile, row, true);
+        for (int tile = 0; tile < tiles; ++tile, ++seq) {
+          const TilePoint cur = tile_point<kExport>(a, ray0, pts, S, tile, row, true);
 #pragma unroll
-        for (int li = 0; li < 8; ++li) {
-          if (issued >= kDepth) {
-            long long t0 = 0;
-            if (prof) t0 = clock64();
-            cp_async_wait<kDepth - 1>();
-            if (prof) t_wait_b += clock64() - t0;
-            blend_item((li - kDepth + 8) & 7);
-            if (((li - kDepth + 8) & 7) == 7) finish_tile(prev, prev_seq);  // level 7 retires at li == kDepth - 1 of the NEXT tile
+          for (int li = 0; li < kLv; ++li) {
+            const int l = l0 + li;
+            const LevelCell c = level_cell(cur.pos, F.scalings[l]);
+            const uint32_t base = (uint32_t)l << F.log2T;
+            // x-neighbours (floor x even, ceil = floor + 1) are adjacent table rows r, r^1: one 16-byte load fetches both; only
+            // lanes with an odd floor x load the ceil-x row separately.  Corner pairs (x floor, x ceil) per (y,z): (6,5) (7,4) (2,1) (3,0).
+            const bool pair = ((c.hx[0] & 1u) == 0u) && (c.hx[1] == c.hx[0] + 1u);
+            constexpr int kf[4] = {6, 7, 2, 3}, kc[4] = {5, 4, 1, 0};
+            float2 f[8];
+            float4 pv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t rf = corner_row(c, kf[q], hmask, base);
+              if (kDbg && (a.debug & 4)) {
+                pv[q] = make_float4(c.ox, c.oy, c.oz, 1.f);
+                f[kc[q]] = make_float2(c.oy, c.oz);
+                continue;
+              }
+              pv[q] = __ldg(reinterpret_cast<const float4*>(table + (rf & ~1u)));
+              if (!pair) f[kc[q]] = __ldg(table + corner_row(c, kc[q], hmask, base));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t rf = corner_row(c, kf[q], hmask, base);
+              const bool f_first = (rf & 1u) == 0u;
+              f[kf[q]] = f_first ? make_float2(pv[q].x, pv[q].y) : make_float2(pv[q].z, pv[q].w);
+              if (pair) f[kc[q]] = f_first ? make_float2(pv[q].z, pv[q].w) : make_float2(pv[q].x, pv[q].y);
+            }
+            const float2 r = trilerp(f, c);
+            enc[2 * li] = r.x;
+            enc[2 * li + 1] = r.y;
           }
-          issue_item(cur, li);
+          finish_tile(cur, seq);
         }
-        prev = cur;
-        prev_seq = seq;
       }
-    }
-    // drain: the last kDepth items (all of the last tile when kDepth <= 8)
-    if (prev_seq >= 0) {
-      cp_async_wait<0>();
+      if (prof) printf("fwd coarse gather warp: total %lld cycles, waiting for a free encoding buffer %lld\n", clock64() - t_total, t_wait_a);
+    } else {
+      // ---- fine levels: every lane hits its own table lines, so nothing coalesces; rows are staged with cp.async (rows in flight cost
+      // shared memory, not registers) kDepth (tile, level) items ahead of their blend
+      int issued = 0;       // items issued so far (stage = issued % kDepth)
+      TilePoint prev{};     // the tile whose last levels are still in flight
+      int prev_seq = -1;
+
+      auto issue_item = [&](const TilePoint& tp, int li) {
+        const int l = l0 + li;
+        const LevelCell c = level_cell(tp.pos, F.scalings[l]);
+        const uint32_t base = (uint32_t)l << F.log2T;
+        const bool pair = ((c.hx[0] & 1u) == 0u) && (c.hx[1] == c.hx[0] + 1u);
+        constexpr int kf[4] = {6, 7, 2, 3}, kc[4] = {5, 4, 1, 0};
+        const uint32_t st = stage0 + (uint32_t)(issued % kDepth) * STAGE_BYTES;
+        uint32_t flags = pair ? 1u : 0u;
 #pragma unroll
-      for (int li = 8 - kDepth; li < 8; ++li) {
-        blend_item(li);
-        ++issued;  // walk the stages in issue order
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t rf = corner_row(c, kf[q], hmask, base);
+          flags |= (rf & 1u) << (1 + q);
+          if (kDbg && (a.debug & 2)) continue;
+          cp_async16(st + STAGE_PAIR + q * 512 + lane * 16, table + (rf & ~1u));
+          cp_async8_if(!pair, st + STAGE_SINGLE + q * 256 + lane * 8, table + corner_row(c, kc[q], hmask, base));
+        }
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + STAGE_META + lane * 16), "f"(c.ox), "f"(c.oy), "f"(c.oz),
+                     "f"(__uint_as_float(flags))
+                     : "memory");
+        cp_async_commit();
+        ++issued;
+      };
+      // blend the item issued kDepth items ago (stage = issued % kDepth, the one the next issue overwrites) -> enc[2 li ..]
+      auto blend_item = [&](int li) {
+        const uint32_t st = stage0 + (uint32_t)(issued % kDepth) * STAGE_BYTES;
+        float ox, oy, oz, fl;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(ox), "=f"(oy), "=f"(oz), "=f"(fl) : "r"(st + STAGE_META + lane * 16) : "memory");
+        const uint32_t flags = __float_as_uint(fl);
+        const bool pair = flags & 1u;
+        constexpr int kf[4] = {6, 7, 2, 3}, kc[4] = {5, 4, 1, 0};
+        float2 f[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 pv;
+          float2 sv;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(pv.x), "=f"(pv.y), "=f"(pv.z), "=f"(pv.w) : "r"(st + STAGE_PAIR + q * 512 + lane * 16) : "memory");
+          asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(sv.x), "=f"(sv.y) : "r"(st + STAGE_SINGLE + q * 256 + lane * 8) : "memory");
+          const bool f_first = ((flags >> (1 + q)) & 1u) == 0u;
+          f[kf[q]] = f_first ? make_float2(pv.x, pv.y) : make_float2(pv.z, pv.w);
+          const float2 nb = f_first ? make_float2(pv.z, pv.w) : make_float2(pv.x, pv.y);
+          f[kc[q]] = pair ? nb : sv;
+        }
+        LevelCell c;
+        c.ox = ox;
+        c.oy = oy;
+        c.oz = oz;
+        const float2 r = trilerp(f, c);
+        enc[2 * li] = r.x;
+        enc[2 * li + 1] = r.y;
+      };
+
+      for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
+        const int ray0 = group * G;
+        const int pts = min(G, R - ray0) * S;
+        const int tiles = (pts + 127) / 128;
+#pragma unroll 1
+        for (int tile = 0; tile < tiles; ++tile, ++seq) {
+          const TilePoint cur = tile_point<kExport>(a, ray0, pts, S, tile, row, true);
+#pragma unroll
+          for (int li = 0; li < kLv; ++li) {
+            if (issued >= kDepth) {
+              long long t0 = 0;
+              if (prof) t0 = clock64();
+              cp_async_wait<kDepth - 1>();
+              if (prof) t_wait_b += clock64() - t0;
+              constexpr int kBack = kLv - kDepth;  // the retired item is level (li + kBack) % kLv: of this tile if li >= kDepth, else of the previous
+              blend_item((li + kBack) % kLv);
+              if ((li + kBack) % kLv == kLv - 1) finish_tile(prev, prev_seq);  // the last level retires at li == kDepth - 1 of the NEXT tile
+            }
+            issue_item(cur, li);
+          }
+          prev = cur;
+          prev_seq = seq;
+        }
       }
-      finish_tile(prev, prev_seq);
+      // drain: the last kDepth items (all of the last tile when kDepth == kLv)
+      if (prev_seq >= 0) {
+        cp_async_wait<0>();
+#pragma unroll
+        for (int li = kLv - kDepth; li < kLv; ++li) {
+          blend_item(li);
+          ++issued;  // walk the stages in issue order
+        }
+        finish_tile(prev, prev_seq);
+      }
+      if (prof) printf("fwd fine gather warp: total %lld cycles, waiting for a free encoding buffer %lld, for cp.async data %lld\n", clock64() - t_total, t_wait_a, t_wait_b);
     }
-    if (prof) printf("fwd gather warp: total %lld cycles, waiting for a free encoding buffer %lld, for cp.async data %lld\n", clock64() - t_total, t_wait_a, t_wait_b);
   } else {
     // ========================= chain warps =========================
     reg_inc<kChainRegs>();
@@ -406,6 +504,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_ws_kernel(co
     const int bar_id = BAR_SLOT0 + slot;
 
 #define FNR_SLOT_ISSUE(...)              \
+  if (prof) t_mark = clock64();          \
   tmem_st_wait();                        \
   fence_before_sync();                   \
   named_bar_sync(bar_id, kSlotThreads);  \
@@ -416,11 +515,15 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_ws_kernel(co
       mma_commit(bar);                   \
     }                                    \
     __syncwarp();                        \
-  }
-#define FNR_SLOT_WAIT()  \
-  mbar_wait(bar, phase); \
-  phase ^= 1;            \
-  fence_after_sync();
+  }                                      \
+  if (prof) t_wait_c += clock64() - t_mark;
+#define FNR_SLOT_WAIT()                    \
+  if (prof) t_mark = clock64();            \
+  mbar_wait(bar, phase);                   \
+  phase ^= 1;                              \
+  fence_after_sync();                      \
+  if (prof) t_wait_d += clock64() - t_mark;
+    long long t_mark = 0;
 
     int seq = 0;
     for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
@@ -436,10 +539,19 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_ws_kernel(co
         {
           long long t0 = 0;
           if (prof) t0 = clock64();
-          mbar_wait(&s_full[e], (uint32_t)(use & 1));  // the gather warps have written this tile's encoding + selectors
+          mbar_wait_sleep(&s_full[e], (uint32_t)(use & 1));  // the gather warps have written this tile's encoding + selectors
           if (prof) t_wait_a += clock64() - t0;
         }
         const bool sel = s_sel[e * 128 + row] != 0;
+        if (kDbg && (a.debug & 8)) {
+          named_bar_sync(bar_id, kSlotThreads);
+          if (issue_warp && lane == 0) mbar_arrive(&s_empty[e]);
+          if (half == 0 && tp.valid) {
+            float* q = s_samples + 5 * tp.local;
+            q[0] = sel ? 1.f : 0.f; q[1] = q[2] = q[3] = 0.5f; q[4] = 0.f;
+          }
+          continue;
+        }
         // ---- base0 (A = encoding ring buffer); its completion also frees the buffer for the gather warps
         if (issue_warp) {
           if (elect_one_sync()) {
@@ -561,7 +673,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_ws_kernel(co
     }
 #undef FNR_SLOT_ISSUE
 #undef FNR_SLOT_WAIT
-    if (prof) printf("fwd chain slot %d: total %lld cycles, waiting for encodings %lld, group stage (incl. its barriers) %lld\n", slot, clock64() - t_total, t_wait_a, t_wait_b);
+    if (prof)
+      printf("fwd chain slot %d: total %lld cycles, waiting for encodings %lld, group stage (incl. its barriers) %lld, operand sync + MMA issue %lld, "
+             "waiting for MMA completion %lld\n", slot, clock64() - t_total, t_wait_a, t_wait_b, t_wait_c, t_wait_d);
   }
 
   fence_before_sync();
@@ -585,11 +699,11 @@ int pick_rays_per_group_ws(int S) {
   return best;
 }
 
-template <bool kExport>
+template <bool kExport, bool kDbg>
 int configure_ws() {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_render_forward_ws_kernel<kExport>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(tc_render_forward_ws_kernel<kExport, kDbg>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tc_render_forward_ws_kernel)");
     configured = true;
   }
@@ -603,7 +717,8 @@ bool tc_ws_supported(int S) { return S >= 1 && S <= kMaxGroupPoints; }
 int launch_tc_render_forward_ws(const KField& F, const KParams& P, const KRays& Rr, const KFieldOut& O, const KComposite& Cm,
                                 cudaStream_t st) {
   if (Rr.R == 0) return FNR_OK;
-  if (int rc = configure_ws<false>()) return rc;
+  const int debug = getenv("FNR_DEBUG_FWD") ? atoi(getenv("FNR_DEBUG_FWD")) : 0;
+  if (int rc = debug ? configure_ws<false, true>() : configure_ws<false, false>()) return rc;
   WsArgs a;
   memset(&a.E, 0, sizeof(a.E));
   a.F = F;
@@ -612,17 +727,18 @@ int launch_tc_render_forward_ws(const KField& F, const KParams& P, const KRays& 
   a.O = O;
   a.Cm = Cm;
   a.rays_per_group = pick_rays_per_group_ws(Rr.S);
-  a.debug = getenv("FNR_DEBUG_FWD") != nullptr;
+  a.debug = debug;
   a.composite = Cm.rgb || Cm.accumulation || Cm.depth || Cm.depth_index || Cm.semantics || Cm.weights;
   const int groups = (Rr.R + a.rays_per_group - 1) / a.rays_per_group;
   const int grid = groups < sm_count() ? groups : sm_count();
-  tc_render_forward_ws_kernel<false><<<grid, kCtaThreads, kSmemBytes, st>>>(a);
-  return check_cuda(cudaGetLastError(), "tc_render_forward_ws_kernel");
+  if (debug) tc_render_forward_ws_kernel<false, true><<<grid, kCtaThreads, kSmemBytes, st>>>(a);
+  else tc_render_forward_ws_kernel<false, false><<<grid, kCtaThreads, kSmemBytes, st>>>(a);
+  return check_launch("tc_render_forward_ws_kernel");
 }
 
 int launch_tc_export_ws(const KField& F, const KParams& P, const KExport& E, cudaStream_t st) {
   if (E.B == 0) return FNR_OK;
-  if (int rc = configure_ws<true>()) return rc;
+  if (int rc = configure_ws<true, false>()) return rc;
   WsArgs a;
   memset(&a, 0, sizeof(a));
   a.F = F;
@@ -633,8 +749,8 @@ int launch_tc_export_ws(const KField& F, const KParams& P, const KExport& E, cud
   a.rays_per_group = pick_rays_per_group_ws(E.S);
   const int groups = (E.B + a.rays_per_group - 1) / a.rays_per_group;
   const int grid = groups < sm_count() ? groups : sm_count();
-  tc_render_forward_ws_kernel<true><<<grid, kCtaThreads, kSmemBytes, st>>>(a);
-  return check_cuda(cudaGetLastError(), "tc_render_forward_ws_kernel<export>");
+  tc_render_forward_ws_kernel<true, false><<<grid, kCtaThreads, kSmemBytes, st>>>(a);
+  return check_launch("tc_render_forward_ws_kernel<export>");
 }
 
 }  // namespace fnr

@@ -26,8 +26,9 @@ def default_loss(outputs: Dict[str, Tensor], image: Tensor, fruit_mask: Tensor, 
 
 class GraphedTrainStep:
     def __init__(self, field, num_rays: int, num_samples: int, impl: int = L.FNR_IMPL_AUTO, semantic_loss_weight: float = 1.0,
-                 use_graph: bool = True):
+                 use_graph: bool = True, flat_grad: Optional[Tensor] = None):
         self.field = field
+        self._flat_grad_buffer = flat_grad  # persistent (e.g. symmetric / multicast-mapped) gradient buffer, or None
         self.impl = impl
         self.semantic_loss_weight = semantic_loss_weight
         dev = next(field.parameters()).device
@@ -59,6 +60,7 @@ class GraphedTrainStep:
         self._copy_stream = None
         self._staging = None
         self._copy_done = None
+        self.launches_per_step = 0
 
     # ---- inputs -----------------------------------------------------------------------------------
     def load_batch(self, origins, directions, starts, ends, camera_indices, image, fruit_mask, non_blocking: bool = True) -> int:
@@ -112,7 +114,7 @@ class GraphedTrainStep:
         for p in self.params:
             p.grad = None
         out = ops.render(f.kernel_shape(), self.params, st["origins"], st["directions"], st["starts"], st["ends"], st["camera_indices"],
-                         f.position_mode(), f.appearance_mode(), impl=self.impl)
+                         f.position_mode(), f.appearance_mode(), impl=self.impl, flat_grad=self._flat_grad_buffer)
         loss = default_loss(out, st["image"], st["fruit_mask"], self.semantic_loss_weight)
         loss.backward()
         self.outputs, self.loss = out, loss.detach()
@@ -121,6 +123,10 @@ class GraphedTrainStep:
 
     def capture(self, warmup: int = 3) -> None:
         if not self.use_graph:
+            lib = L.load()
+            lib.fnr_launch_count(1)
+            self._eager()
+            self.launches_per_step = int(lib.fnr_launch_count(1))
             self._captured = True
             return
         side = torch.cuda.Stream(device=self.device)
@@ -133,8 +139,11 @@ class GraphedTrainStep:
         for p in self.params:
             p.grad = None
         self.graph = torch.cuda.CUDAGraph()
+        lib = L.load()
+        lib.fnr_launch_count(1)
         with torch.cuda.graph(self.graph):
             self._eager()
+        self.launches_per_step = int(lib.fnr_launch_count(1))  # kernels of THIS library recorded into the step's graph
         self._captured = True
 
     def __call__(self) -> Tensor:

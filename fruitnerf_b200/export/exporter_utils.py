@@ -98,8 +98,10 @@ def sample_volume(pipeline, num_points: int, output_dir: Optional[pathlib.Path] 
             full = rows[:, 3:7]
             colors = (full / full.max())[:, :3]  # exporter_utils.py:203, 228: normalise by the max over rgb+alpha
         path = None
-        if output_dir is not None and config is not None:
-            path = str(pathlib.Path(output_dir) / config.load_dir.parts[-3] / f"{name}.ply")
+        if output_dir is not None and config is not None and getattr(config, "load_dir", None) is not None:
+            parts = pathlib.Path(config.load_dir).parts  # upstream: outputs/<experiment>/<method>/<timestamp>/nerfstudio_models
+            sub = parts[-3] if len(parts) >= 3 else ""
+            path = str(pathlib.Path(output_dir) / sub / f"{name}.ply")
         out[name] = {"points": rows[:, :3] * scale, "colors": colors, "alpha": rows[:, 6], "path": path}
     return out
 

@@ -117,6 +117,10 @@ class FruitModel(nn.Module):
     def populate_modules(self):
         """fruit_nerf.py:78-177."""
         cfg = self.config
+        if cfg.use_gradient_scaling:
+            # nerfacto's scale_gradients_by_distance_squared hook between the field and the renderers: the fused kernel has
+            # no such stage, and silently training without it would not be the configuration that was asked for
+            raise NotImplementedError("use_gradient_scaling=True is not implemented by the fused render kernels (reference default: False)")
         scene_contraction = None if cfg.disable_scene_contraction else SceneContraction(order=float("inf"))
         self.field = FruitField(
             self.scene_box.aabb,
@@ -192,7 +196,10 @@ class FruitModel(nn.Module):
         if ray_bundle.nears is not None and ray_bundle.fars is not None:
             return ray_bundle
         ones = torch.ones_like(ray_bundle.origins[..., 0:1])
-        ray_bundle.nears = ones * self.near_plane
+        # NearFarCollider.set_nears_and_fars: `near_plane = self.near_plane if self.training else 0` -- evaluation and
+        # inference renders start sampling at the camera centre
+        near_plane = self.near_plane if self.training else 0.0
+        ray_bundle.nears = ones * near_plane
         ray_bundle.fars = ones * self.far_plane
         return ray_bundle
 

@@ -1,7 +1,16 @@
-"""Method specifications of the plugin (fruit_nerf/fruit_nerf_config.py:27-164), restated as plain
-dataclasses.  With nerfstudio installed these are wrapped into ``MethodSpecification`` objects and
-discovered through the ``nerfstudio.method_configs`` entry points (pyproject.toml); without it they
-still carry every hyper-parameter of the three shipped configs."""
+"""Method specifications of the plugin (fruit_nerf/fruit_nerf_config.py:27-164).
+
+``TrainerSpec`` restates the TrainerConfig fields the reference sets as plain dataclasses: it is what
+``fruitnerf_b200.trainer.Trainer`` consumes and what ``METHODS`` holds, with or without nerfstudio.
+
+The ``nerfstudio.method_configs`` entry points (pyproject.toml) resolve to the module attributes
+``fruit_nerf_method`` / ``fruit_nerf_method_big`` / ``fruit_nerf_method_huge``.  When nerfstudio is importable
+these are ``MethodSpecification(config=TrainerConfig(...))`` objects built by ``method_specification`` (same
+``method_name``, iteration counts, pipeline config and per-group optimizer / scheduler configs as the reference,
+fruit_nerf_config.py:27-61 / 63-111 / 113-164), so ``ns-train fruit_nerf`` discovers them and drives
+``FruitPipeline`` with its own trainer and torch optimizers (the kernels expose ordinary ``.grad``s through
+``ops.render``'s autograd function).  Without nerfstudio the same names are the plain ``TrainerSpec``s.  The
+nerfstudio branch cannot be exercised in this image (the package is not installable offline): INTEGRATION.md."""
 from __future__ import annotations
 
 from dataclasses import dataclass, field
@@ -86,3 +95,42 @@ fruit_nerf_method_huge = TrainerSpec(
 )
 
 METHODS = {m.method_name: m for m in (fruit_nerf_method, fruit_nerf_method_big, fruit_nerf_method_huge)}
+
+
+def method_specification(spec: TrainerSpec):
+    """``MethodSpecification`` of a TrainerSpec for nerfstudio's plugin discovery (fruit_nerf_config.py:27, 63, 113)."""
+    from nerfstudio.configs.base_config import ViewerConfig  # type: ignore
+    from nerfstudio.engine.optimizers import AdamOptimizerConfig, RAdamOptimizerConfig  # type: ignore
+    from nerfstudio.engine.schedulers import ExponentialDecaySchedulerConfig  # type: ignore
+    from nerfstudio.engine.trainer import TrainerConfig  # type: ignore
+    from nerfstudio.plugins.types import MethodSpecification  # type: ignore
+
+    kinds = {"Adam": AdamOptimizerConfig, "RAdam": RAdamOptimizerConfig}
+    optimizers = {}
+    for group, o in spec.optimizers.items():
+        sched = o["scheduler"]
+        optimizers[group] = {
+            "optimizer": kinds[o["optimizer"]["type"]](lr=o["optimizer"]["lr"], eps=o["optimizer"]["eps"]),
+            "scheduler": None if sched is None else ExponentialDecaySchedulerConfig(lr_final=sched["lr_final"], max_steps=sched["max_steps"]),
+        }
+    config = TrainerConfig(
+        method_name=spec.method_name,
+        steps_per_eval_batch=spec.steps_per_eval_batch,
+        steps_per_save=spec.steps_per_save,
+        max_num_iterations=spec.max_num_iterations,
+        mixed_precision=spec.mixed_precision,
+        pipeline=spec.pipeline,
+        optimizers=optimizers,
+        viewer=ViewerConfig(num_rays_per_chunk=1 << 15),
+        vis="viewer",
+    )
+    return MethodSpecification(config=config, description=spec.description)
+
+
+try:  # pragma: no cover - nerfstudio is not installable in this image
+    import nerfstudio.plugins.types  # type: ignore  # noqa: F401
+
+    fruit_nerf_method, fruit_nerf_method_big, fruit_nerf_method_huge = (
+        method_specification(METHODS[n]) for n in ("fruit_nerf", "fruit_nerf_big", "fruit_nerf_huge"))
+except ImportError:
+    pass

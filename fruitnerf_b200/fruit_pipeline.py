@@ -117,14 +117,29 @@ class FruitPipeline(nn.Module):
         if flat is not None:
             sync_gradients(flat, self.world_size)
 
-    def load_pipeline(self, loaded_state: Dict[str, Any], step: int) -> None:
-        """fruit_pipeline.py:229-240: strip DDP's ``module.`` prefix, strict load."""
+    # keys a nerfstudio-written FruitNeRF checkpoint holds that have no counterpart here: metric modules of the model
+    # (fruit_nerf.py:174-177) and the datamanager's camera optimiser / ray generators
+    REFERENCE_ONLY_PREFIXES = ("_model.lpips.", "_model.psnr.", "_model.ssim.", "_model.collider.", "datamanager.train_camera_optimizer.",
+                               "datamanager.train_ray_generator.", "datamanager.eval_ray_generator.", "datamanager.orthographic_ray_generator.")
+
+    def load_pipeline(self, loaded_state: Dict[str, Any], step: int, strict: bool = True) -> None:
+        """fruit_pipeline.py:229-240: strip DDP's ``module.`` prefix, strict load.  ``strict=False`` is the loader for
+        checkpoints the REFERENCE wrote with ``implementation='torch'``: keys of modules that only exist upstream
+        (``REFERENCE_ONLY_PREFIXES``) are dropped, everything else must still match name by name and shape by shape
+        (tinycudann checkpoints store packed fp16 ``params`` blobs and cannot be mapped)."""
         state = {(key[len("module."):] if key.startswith("module.") else key): value for key, value in loaded_state.items()}
         self.model.update_to_step(step)
+        if not strict:
+            state = {k: v for k, v in state.items() if not k.startswith(self.REFERENCE_ONLY_PREFIXES)}
+            if any(k.endswith(".params") for k in state):
+                raise ValueError("tinycudann checkpoint (packed fp16 `params` tensors): retrain or export with implementation='torch'")
         self.load_state_dict(state, strict=True)
 
     def get_training_callbacks(self, training_callback_attributes) -> List:
-        return self.datamanager.get_training_callbacks(training_callback_attributes)
+        """fruit_pipeline.py:242-249: datamanager callbacks followed by the model's (proposal-weight annealing)."""
+        datamanager_callbacks = self.datamanager.get_training_callbacks(training_callback_attributes)
+        model_callbacks = self.model.get_training_callbacks(training_callback_attributes)
+        return list(datamanager_callbacks) + list(model_callbacks)
 
     def get_param_groups(self) -> Dict[str, List[Parameter]]:
         """fruit_pipeline.py:251-260."""

@@ -115,14 +115,27 @@ def _stream(dev: torch.device) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
 
 
-def flat_zero_grads(tensors: Sequence[Tensor]) -> Tuple[Tensor, List[Tensor]]:
+def flat_grad_numel(tensors: Sequence[Tensor]) -> int:
+    """Elements of the flat gradient buffer of these parameters (every view 16-byte aligned)."""
+    return sum((t.numel() + 3) // 4 * 4 for t in tensors)
+
+
+def flat_zero_grads(tensors: Sequence[Tensor], out: Optional[Tensor] = None) -> Tuple[Tensor, List[Tensor]]:
     """One flat, zero-filled fp32 buffer with a 16-byte aligned view per parameter.  The backward
-    kernels accumulate straight into it; the multi-GPU path all-reduces it in one collective."""
+    kernels accumulate straight into it; the multi-GPU path all-reduces it in one collective.  ``out``: a persistent
+    buffer of the caller (e.g. the symmetric allocation of the NVLS gradient exchange) that is re-zeroed instead of
+    allocating a new one every step."""
     offs, total = [], 0
     for t in tensors:
         offs.append(total)
         total += (t.numel() + 3) // 4 * 4
-    flat = torch.zeros(total, dtype=torch.float32, device=tensors[0].device)
+    if out is not None:
+        if out.dtype != torch.float32 or out.numel() < total or out.device != tensors[0].device or not out.is_contiguous():
+            raise ValueError(f"flat gradient buffer must be contiguous fp32 with >= {total} elements on {tensors[0].device}")
+        flat = out
+        flat.zero_()
+    else:
+        flat = torch.zeros(total, dtype=torch.float32, device=tensors[0].device)
     views = [flat[o : o + t.numel()].view_as(t) for o, t in zip(offs, tensors)]
     return flat, views
 
@@ -191,7 +204,7 @@ class _Render(torch.autograd.Function):
         gs = [None if t is None else _f32c(t) for t in (g_rgb, g_acc, g_sem, g_w, g_sd, g_srgb, g_ssem)]
         desc = shape.desc(mode["position_mode"], mode["appearance_mode"], mode.get("bwd_impl", mode.get("impl", L.FNR_IMPL_AUTO)))
         pstruct = _params_struct(shape, params)
-        flat, views = flat_zero_grads(params)
+        flat, views = flat_zero_grads(params, out=mode.get("flat_grad"))
         gstruct = _params_struct(shape, views)
         rays = L.RayBatch(R, S, _ptr(origins), _ptr(directions), _ptr(starts), _ptr(ends), _ptr(cam))
         saved = L.RenderSaved(_ptr(w), _ptr(sd), _ptr(srgb), _ptr(ssem), _ptr(stash), _ptr(acc))
@@ -211,12 +224,14 @@ class _Render(torch.autograd.Function):
 
 def render(shape: FieldShape, params: Sequence[Tensor], origins: Tensor, directions: Tensor, starts: Tensor, ends: Tensor,
            camera_indices: Optional[Tensor], position_mode: int, appearance_mode: int, clamp_rgb: bool = False,
-           impl: int = L.FNR_IMPL_AUTO) -> Dict[str, Tensor]:
+           impl: int = L.FNR_IMPL_AUTO, flat_grad: Optional[Tensor] = None) -> Dict[str, Tensor]:
     """Fused FruitField.forward + get_weights + renderers (fruit_nerf/fruit_nerf.py:320-348).
 
-    origins/directions [R,3]; starts/ends [R,S]; camera_indices [R] or None.
+    origins/directions [R,3]; starts/ends [R,S]; camera_indices [R] or None.  ``flat_grad``: persistent flat gradient
+    buffer the backward accumulates into (``flat_zero_grads``).
     """
-    mode = dict(composite=True, position_mode=position_mode, appearance_mode=appearance_mode, clamp_rgb=clamp_rgb, impl=impl)
+    mode = dict(composite=True, position_mode=position_mode, appearance_mode=appearance_mode, clamp_rgb=clamp_rgb, impl=impl,
+                flat_grad=flat_grad)
     rgb, acc, depth, didx, sem, w, sd, srgb, ssem = _Render.apply(shape, mode, origins, directions, starts, ends, camera_indices, *params)
     return {
         "rgb": rgb,

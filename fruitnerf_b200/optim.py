@@ -152,6 +152,24 @@ class FusedAdam:
         return {"step": self.step_count, "sched_step": self.sched_step, "exp_avg": [t.clone() for t in self.exp_avg], "exp_avg_sq": [t.clone() for t in self.exp_avg_sq]}
 
     def load_state_dict(self, sd: Dict) -> None:
+        if "state" in sd and "param_groups" in sd:
+            # torch.optim.Adam / RAdam state_dict() as nerfstudio's Optimizers checkpoint it: state[i] = {step, exp_avg, exp_avg_sq}
+            # in parameter order; the scheduler position is restored by the trainer (it follows the trainer step)
+            steps = []
+            for i, (m, v) in enumerate(zip(self.exp_avg, self.exp_avg_sq)):
+                st = sd["state"].get(i)
+                if st is None:
+                    m.zero_()
+                    v.zero_()
+                    continue
+                m.copy_(st["exp_avg"])
+                v.copy_(st["exp_avg_sq"])
+                steps.append(int(st["step"]))
+            if len(set(steps)) > 1:
+                raise ValueError(f"per-parameter step counts differ ({sorted(set(steps))}): the fused update keeps one count per group")
+            self.step_count = steps[0] if steps else 0
+            self.sched_step = self.step_count
+            return
         self.step_count = int(sd["step"])
         self.sched_step = int(sd.get("sched_step", sd["step"]))
         for dst, src in zip(self.exp_avg, sd["exp_avg"]):

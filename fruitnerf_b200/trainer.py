@@ -32,13 +32,25 @@ class Trainer:
                  use_cuda_graph: bool = False, graph_warmup: int = 3):
         self.spec = spec
         self.device = torch.device(device)
+        if self.device.type == "cuda":
+            # the native launchers use the CURRENT device (one process per GPU): make it the trainer's
+            torch.cuda.set_device(self.device)
         self.world_size, self.local_rank = world_size, local_rank
         self.output_dir = pathlib.Path(output_dir) if output_dir else None
         self.pipeline = spec.pipeline.setup(device=self.device, test_mode="val", world_size=world_size, local_rank=local_rank)
         self.pipeline.train()
+        if world_size > 1 and dist.is_available() and dist.is_initialized():
+            # DDP broadcasts rank 0's parameters and buffers at construction (fruit_pipeline.py:117): replicas must start
+            # identical because only gradients are exchanged afterwards
+            with torch.no_grad():
+                for t in list(self.pipeline.parameters()) + list(self.pipeline.buffers()):
+                    if t.numel():
+                        dist.broadcast(t.data, src=0)
+        if self.output_dir is not None and local_rank == 0:
+            self.save_config()
         self.param_groups = self.pipeline.get_param_groups()
         self.optimizers: Dict[str, FusedAdam] = build_optimizers(self.param_groups, spec.optimizers)
-        self.callbacks: List[Dict] = list(self.pipeline.model.get_training_callbacks(None)) + list(self.pipeline.get_training_callbacks(None))
+        self.callbacks: List[Dict] = list(self.pipeline.get_training_callbacks(None))  # datamanager + model (fruit_pipeline.py:242-249)
         self.step = 0
         self.use_cuda_graph = bool(use_cuda_graph) and self.device.type == "cuda"
         self.graph_warmup = graph_warmup
@@ -171,6 +183,24 @@ class Trainer:
                 self.save_checkpoint()
         return history
 
+    # ---- config.yml (nerfstudio TrainerConfig.save_config): what eval_setup / ns-export-semantics load back ------------
+    def save_config(self) -> pathlib.Path:
+        import yaml
+
+        self.output_dir.mkdir(parents=True, exist_ok=True)
+        path = self.output_dir / "config.yml"
+        path.write_text(yaml.dump(self.spec))
+        outs = getattr(self.pipeline.datamanager, "train_dataparser_outputs", None)
+        if outs is not None:
+            outs.save_dataparser_transform(self.output_dir / "dataparser_transforms.json")
+        else:  # in-memory scene: identity transform, the data set's own scale
+            import json
+
+            scale = float(getattr(self.pipeline.datamanager.train_dataset, "dataparser_scale", 1.0))
+            (self.output_dir / "dataparser_transforms.json").write_text(
+                json.dumps({"transform": [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]], "scale": scale}, indent=4))
+        return path
+
     # ---- checkpoints (nerfstudio Trainer.save_checkpoint / _load_checkpoint) --------------------------------------
     def save_checkpoint(self, path: Optional[str] = None) -> pathlib.Path:
         if path is None:
@@ -189,6 +219,7 @@ class Trainer:
         self.pipeline.load_pipeline(state["pipeline"], self.step)
         for k, o in self.optimizers.items():
             o.load_state_dict(state["optimizers"][k])
+            o.sched_step = self.step  # schedules follow the trainer step
         sampler = getattr(self.pipeline.model, "proposal_sampler", None)
         if hasattr(sampler, "step_cb"):
             sampler._step = self.step

@@ -289,6 +289,10 @@ int fnr_ray_metrics(const float* weights, const float* sdist, const float* start
                     int32_t num_samples, float* distortion, float* median_depth, void* stream);
 
 int fnr_version(void);
+
+/* Number of CUDA kernels this library has launched (or recorded into a stream capture) in this process since the
+ * last call with reset != 0.  Diagnostic only: lets a benchmark report how many of ITS kernels a step consists of. */
+uint64_t fnr_launch_count(int32_t reset);
 const char* fnr_last_error(void);
 
 /* FruitModel.get_outputs minus the sampler: field + compositing, fused. */
@@ -314,6 +318,26 @@ int fnr_export_forward(const fnr_field_desc* desc, const fnr_field_params* param
                        const float* normal, const float* bins, float near_plane, float far_plane,
                        int32_t num_rays, int32_t num_samples, uint64_t point_base,
                        const fnr_export_params* xp, const fnr_export_out* out, void* stream);
+
+/* ---- gradient exchange of the data-parallel path (fruit_nerf/fruit_pipeline.py:116-118: DDP's all-reduce) as one kernel over
+ * NVSwitch multicast memory.  The caller owns a SYMMETRIC allocation (every rank maps its own copy and the multicast object
+ * spanning all copies; with PyTorch: torch.distributed._symmetric_memory.empty + rendezvous) and passes its addresses. ---- */
+typedef struct fnr_nvls_desc {
+  void* multicast_ptr;               /* multicast address of the fp32 gradient region */
+  void* local_ptr;                   /* this rank's own (unicast) address of the same region */
+  void* multicast_bf16;              /* bf16 staging region (numel bf16 elements) for wire_bf16, or NULL */
+  void* local_bf16;
+  void* const* signal_pads;          /* DEVICE array [world_size]: uint32 signal pad of every rank, zero-initialised */
+  void* grid_counter;                /* device uint32, zero before the first call (wire_bf16 only), or NULL */
+  int32_t rank, world_size;
+  int32_t signal_slots;              /* uint32 slots in each pad */
+  int32_t signal_slot_base;          /* first slot this library may use (64 blocks x world_size slots from there) */
+} fnr_nvls_desc;
+
+/* In place: region[i] = mean over ranks of region[i], i < numel (numel % (8 * world_size) == 0).  Every rank calls it with
+ * the same numel; the kernels of all ranks meet on the signal pads, so all ranks must launch it (like a collective).
+ * wire_bf16 != 0: operands cross the links as bf16 (fp32 accumulation in the switch), result rounded to bf16. */
+int fnr_nvls_allreduce_mean(const fnr_nvls_desc* d, size_t numel, int32_t wire_bf16, void* stream);
 
 /* Hash-grid row indices (exact-integer parity hook): rows[N,L,8] in nerfstudio corner order for
  * the masked [0,1]^3 positions of the given samples; also writes positions[N,3] if non-NULL. */

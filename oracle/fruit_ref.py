@@ -164,10 +164,11 @@ def loss_dict(outputs: Dict[str, Tensor], image: Tensor, fruit_mask: Tensor, sem
     }
 
 
-def export_outputs(params, spec, origins, directions, nears, fars, num_samples: int, chunk: int = 32768):
+def export_outputs(params, spec, origins, directions, nears, fars, num_samples: int, chunk: int = 32768, t_rand=None):
     """FruitModel.get_export_outputs (fruit_nerf.py:251-269) after setup_inference (179-183):
-    uniform bins, field with spatial_distortion=None (aabb normalisation), mean appearance."""
-    starts, ends = ns.uniform_bins(nears, fars, num_samples)
+    uniform bins (jittered by ``t_rand`` when the sampler module is in training mode, see ns.uniform_bins), field with
+    spatial_distortion=None (aabb normalisation), mean appearance."""
+    starts, ends = ns.uniform_bins(nears, fars, num_samples, t_rand)
     B = origins.shape[0]
     o = origins[:, None, :].expand(B, num_samples, 3)
     d = directions[:, None, :].expand(B, num_samples, 3)

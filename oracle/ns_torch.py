@@ -222,10 +222,18 @@ def render_semantics(semantics: Tensor, weights: Tensor) -> Tensor:
 # Export sampling               (components/ray_samplers.py:54-104, ray_generators.py:46-66,
 #                                data/fruit_datamanager.py:42-121)
 # --------------------------------------------------------------------------------------
-def uniform_bins(nears: Tensor, fars: Tensor, num_samples: int) -> Tuple[Tensor, Tensor]:
-    """UniformSamplerWithNoise.generate_ray_samples in eval mode (no jitter; export runs under
-    model.eval()).  nears/fars [B,1] -> (starts [B,S,1], ends [B,S,1])."""
+def uniform_bins(nears: Tensor, fars: Tensor, num_samples: int, t_rand: Tensor = None) -> Tuple[Tensor, Tensor]:
+    """UniformSamplerWithNoise.generate_ray_samples (components/ray_samplers.py:54-104).  nears/fars [B,1] ->
+    (starts [B,S,1], ends [B,S,1]).  ``t_rand`` = None: module in eval mode, the regular grid.  ``t_rand`` [B,S+1] (or
+    [B,1], single_jitter): the stratified jitter of a module in TRAINING mode (ray_samplers.py:78-87) -- the state the
+    reference exporter actually runs it in, because setup_inference() creates the sampler after eval_setup() called
+    pipeline.eval() (scripts/exporter.py:87-95)."""
     bins = torch.linspace(0.0, 1.0, num_samples + 1)[None, ...]
+    if t_rand is not None:
+        bin_centers = (bins[..., 1:] + bins[..., :-1]) / 2.0
+        bin_upper = torch.cat([bin_centers, bins[..., -1:]], -1)
+        bin_lower = torch.cat([bins[..., :1], bin_centers], -1)
+        bins = bin_lower + (bin_upper - bin_lower) * t_rand
     euclid = bins * fars + (1 - bins) * nears  # spacing_fn = identity
     return euclid[..., :-1, None], euclid[..., 1:, None]
 

@@ -33,15 +33,15 @@ def test_struct_sizes_match_header(native_lib):
 
     from fruitnerf_b200 import _lib as L
 
-    src = '#include <stdio.h>\n#include "fruitnerf_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
+    src = '#include <stdio.h>\n#include "fruitnerf_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
           "sizeof(fnr_field_desc),sizeof(fnr_field_params),sizeof(fnr_ray_batch),sizeof(fnr_render_out),sizeof(fnr_render_grads)," \
-          "sizeof(fnr_render_saved),sizeof(fnr_export_params),sizeof(fnr_export_out));return 0;}\n"
+          "sizeof(fnr_render_saved),sizeof(fnr_export_params),sizeof(fnr_export_out),sizeof(fnr_nvls_desc));return 0;}\n"
     with tempfile.TemporaryDirectory() as td:
         c = Path(td) / "s.c"
         c.write_text(src)
         subprocess.run(["gcc", "-I", str(ROOT / "include"), str(c), "-o", str(Path(td) / "s")], check=True)
         sizes = list(map(int, subprocess.run([str(Path(td) / "s")], capture_output=True, text=True, check=True).stdout.split()))
-    mirrors = [L.FieldDesc, L.FieldParams, L.RayBatch, L.RenderOut, L.RenderGrads, L.RenderSaved, L.ExportParams, L.ExportOut]
+    mirrors = [L.FieldDesc, L.FieldParams, L.RayBatch, L.RenderOut, L.RenderGrads, L.RenderSaved, L.ExportParams, L.ExportOut, L.NvlsDesc]
     assert sizes == [C.sizeof(m) for m in mirrors]
 
 

@@ -317,6 +317,44 @@ def test_export_matches_oracle(native_lib, cuda_device, name, n, impl):
 
 
 @pytest.mark.parametrize("impl", IMPLS, ids=IMPL_IDS)
+@pytest.mark.parametrize("name", ["small", "big"])
+def test_export_with_stratified_jitter_matches_oracle(native_lib, cuda_device, name, impl):
+    """The reference exporter's sampler is a module in TRAINING mode (created after eval_setup): every sample is jittered inside
+    its bin (components/ray_samplers.py:78-87).  Same t_rand on both sides -> per-ray bins [B, S+1] through the kernel."""
+    from fruitnerf_b200.components.ray_samplers import UniformSamplerWithNoise
+
+    n = 21
+    sd, spec = make_state(name, table_scale=2.0, weight_gain=2.5)
+    field = make_field(name, sd, spec, cuda_device, contraction=False, test_mode="export").eval()
+    pts, plane = ns.surface_points(((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0)), n)
+    o, dirs, nears, fars = ns.orthographic_rays(pts, plane, batch=10_000, count=1)
+    B = o.shape[0]
+    t_rand = torch.rand((B, n + 1), generator=torch.Generator().manual_seed(5))
+    ref = fr.export_outputs(sd, spec, o, dirs, nears, fars, n, t_rand=t_rand)
+    # the host-side sampler produces the same spacing bins from the same draws (training-mode module)
+    sampler = UniformSamplerWithNoise(num_samples=n, single_jitter=False)
+    assert sampler.training
+    base = torch.linspace(0.0, 1.0, n + 2 - 1)[None]
+    centers = (base[..., 1:] + base[..., :-1]) / 2.0
+    bins = torch.cat([base[..., :1], centers], -1) + (torch.cat([centers, base[..., -1:]], -1) - torch.cat([base[..., :1], centers], -1)) * t_rand
+    buf = ops.ExportBuffers(capacity=B * n, device=cuda_device)
+    dense = ops.export_batch(field.kernel_shape(), field.kernel_params(), o.cuda(), [float(v) for v in dirs[0]], bins.cuda().contiguous(),
+                             float(nears[0]), float(fars[0]), buf, dense_out=True, thresholds=(float(ref["semantics"].median()), float(ref["density"].median()), 0.5),
+                             impl=impl)
+    assert torch.equal(dense["point_location"].cpu(), ref["point_location"]), "jittered sample positions differ bitwise"
+    assert not torch.equal(ref["point_location"], fr.export_outputs(sd, spec, o, dirs, nears, fars, n)["point_location"])
+    assert_rel(dense["density"], ref["density"], what="density")
+    assert_rel(dense["semantics"], ref["semantics"], what="logit")
+    assert_rel(dense["rgb"], ref["rgb"], what="rgb")
+    counts = buf.counts.cpu()
+    keys = buf.keys[2][: int(counts[2])].cpu()
+    rows = buf.rows[2][: int(counts[2])].cpu()
+    assert torch.equal(rows[:, :3], ref["point_location"].reshape(-1, 3)[keys])
+    with pytest.raises(ValueError):
+        ops.export_batch(field.kernel_shape(), field.kernel_params(), o.cuda(), [0.0, 0.0, 1.0], bins[:5].cuda().contiguous(), 0.0, 2.0, buf)
+
+
+@pytest.mark.parametrize("impl", IMPLS, ids=IMPL_IDS)
 def test_full_size_properties(native_lib, cuda_device, impl):
     """BASELINE.json workload (4096 rays x 192 samples): size-independent properties --
     weights in [0,1], accumulation = sum(weights) <= 1, rgb is a convex combination, run-to-run

@@ -89,6 +89,17 @@ def test_model_requires_semantics_metadata_and_builds():
     rb = RayBundle(origins=torch.zeros(4, 3), directions=torch.ones(4, 3))
     rb = m.collider(rb)
     assert torch.all(rb.nears == 0.05) and torch.all(rb.fars == 1000.0)
+    # nerfstudio NearFarCollider: the near plane only applies while training; given nears / fars are kept
+    m.eval()
+    rb = m.collider(RayBundle(origins=torch.zeros(4, 3), directions=torch.ones(4, 3)))
+    assert torch.all(rb.nears == 0.0) and torch.all(rb.fars == 1000.0)
+    rb = m.collider(RayBundle(origins=torch.zeros(4, 3), directions=torch.ones(4, 3), nears=torch.full((4, 1), 0.3), fars=torch.full((4, 1), 2.0)))
+    assert torch.all(rb.nears == 0.3) and torch.all(rb.fars == 2.0)
+    m.train()
+    cfg2 = FruitNerfModelConfig(use_gradient_scaling=True)
+    cfg2.log2_hashmap_size = 10
+    with pytest.raises(NotImplementedError):
+        FruitModel(cfg2, metadata={"semantics": sem}, scene_box=SceneBox(torch.tensor([[-1.0, -1, -1], [1, 1, 1]])), num_train_data=3, test_mode="val")
 
 
 def test_export_grid_matches_oracle_restatement():

@@ -108,8 +108,12 @@ def test_hyper_values_follow_torch_formulas(kind):
     opt.kind = {"Adam": L.FNR_OPT_ADAM, "RAdam": L.FNR_OPT_RADAM}[kind]
     opt.lr, opt.eps, opt.betas, opt.scheduler = 1e-2, 1e-15, (0.9, 0.999), ExponentialDecay(1e-2, 1e-4, 1000)
     for step in (1, 2, 5, 6, 7, 100):
-        h = opt._hyper_values(step, 0.5)
-        assert h[0] == pytest.approx(opt.scheduler.lr(step - 1), rel=1e-6)  # LambdaLR: step k uses lambda(k-1)
+        h = opt._hyper_values(step, 0.5, sched_step=step - 1)
+        assert h[0] == pytest.approx(opt.scheduler.lr(step - 1), rel=1e-6)  # LambdaLR: the k-th iteration uses lambda(k-1)
+        # a group whose optimiser was skipped on some iterations: the lr is read at the TRAINER step, the bias corrections
+        # at the update count (nerfstudio steps every scheduler every iteration, torch skips parameters without a gradient)
+        h2 = opt._hyper_values(step, 0.5, sched_step=6 * step)
+        assert h2[0] == pytest.approx(opt.scheduler.lr(6 * step), rel=1e-6) and h2[4] == h[4] and h2[5] == h[5]
         assert h[4] == pytest.approx(1 - 0.9**step, rel=1e-6) and h[5] == pytest.approx(1 - 0.999**step, rel=1e-5)
         assert h[7] == 0.5
         if kind == "RAdam":
@@ -172,3 +176,115 @@ def test_staged_device_buffer_on_cpu_and_export_slabs():
         slabs = [export_slab(n, world, r) for r in range(world)]
         assert slabs[0][0] == 0 and slabs[-1][1] == n
         assert all(lo <= hi for lo, hi in slabs) and all(slabs[i][1] == slabs[i + 1][0] for i in range(world - 1))
+
+
+def test_dataparser_reads_back_a_written_dataset(tmp_path):
+    """write_dataset -> FruitNerf dataparser (fruit_nerf/data/fruitnerf_dataparser.py:73-292): split, pose pipeline,
+    intrinsics, pixels and {0,1} fruit masks."""
+    from fruitnerf_b200.data.fruitnerf_dataparser import FruitNerf, FruitNerfDataParserConfig, auto_orient_and_center_poses, load_fruit_datasets
+
+    train, ev = make_apple_scene(num_images=20, height=24, width=32, num_fruits=4, seed=2, noise_std=0.0)
+    import dataclasses
+
+    # one data set holding all 20 frames in their original order
+    full_imgs = torch.zeros(20, 24, 32, 3)
+    full_masks = torch.zeros(20, 24, 32, 1)
+    full_c2w = torch.zeros(20, 3, 4)
+    idx = torch.arange(20)
+    full_imgs[idx % 10 != 9], full_imgs[idx % 10 == 9] = train.images, ev.images
+    full_masks[idx % 10 != 9], full_masks[idx % 10 == 9] = train.fruit_masks, ev.fruit_masks
+    full_c2w[idx % 10 != 9], full_c2w[idx % 10 == 9] = train.cameras.camera_to_worlds, ev.cameras.camera_to_worlds
+    full = dataclasses.replace(train, images=full_imgs, fruit_masks=full_masks,
+                               cameras=dataclasses.replace(train.cameras, camera_to_worlds=full_c2w))
+    write_dataset(full, tmp_path / "scene")
+    cfg = FruitNerfDataParserConfig(data=tmp_path / "scene")
+    tr, va, outs = load_fruit_datasets(cfg)
+    # split: ceil(0.9 * 20) = 18 equally spaced training frames (first and last included), the rest held out
+    i_train = np.linspace(0, 19, 18, dtype=int)
+    i_eval = np.setdiff1d(np.arange(20), i_train)
+    assert len(tr) == 18 and len(va) == 2
+    assert [p.name for p in outs.image_filenames] == [f"frame_{i:05d}.png" for i in i_train]
+    # pixels: 8-bit quantisation of the written PNGs; masks exactly {0,1}
+    assert torch.allclose(tr.images, full_imgs[i_train], atol=0.5 / 255 + 1e-6)
+    assert torch.equal(tr.fruit_masks, full_masks[i_train]) and torch.equal(va.fruit_masks, full_masks[i_eval])
+    # poses: "up" orientation + centring on the mean camera + auto-scale into the +/-1 box, applied BEFORE the split
+    m = torch.eye(4).repeat(20, 1, 1)
+    m[:, :3, :4] = full_c2w
+    oriented, transform = auto_orient_and_center_poses(m, "up", "poses")
+    scale = 1.0 / float(oriented[:, :3, 3].abs().max())
+    assert outs.dataparser_scale == pytest.approx(scale, rel=1e-6)
+    want = oriented[i_train].clone()
+    want[:, :3, 3] *= scale
+    assert torch.allclose(tr.cameras.camera_to_worlds, want[:, :3, :4], atol=1e-6)
+    assert float(tr.cameras.camera_to_worlds[:, :, 3].abs().max()) <= 1.0 + 1e-6
+    assert torch.allclose(outs.dataparser_transform, transform)
+    # rotations stay orthonormal, the mean "up" of the cameras points along +z after orientation
+    R = oriented[:, :3, :3]
+    assert torch.allclose(R.transpose(1, 2) @ R, torch.eye(3).expand(20, 3, 3), atol=1e-5)
+    up = oriented[:, :3, 1].mean(0)
+    assert float(up[2] / up.norm()) > 0.999
+    # shared intrinsics, scene box, semantics metadata (classes of fruitnerf_dataparser.py:254)
+    assert (tr.cameras.fx, tr.cameras.height, tr.cameras.width) == (train.cameras.fx, 24, 32)
+    assert torch.equal(tr.scene_box.aabb, torch.tensor([[-1.0, -1, -1], [1, 1, 1]]))
+    assert tr.metadata["semantics"].classes == ["apple", "stuff"] and len(tr.metadata["semantics"].filenames) == 18
+    # the datamanager builds on it and the exporter's transform file round-trips
+    dm = FruitDataManagerConfig(dataparser=cfg).setup(device="cpu")
+    assert len(dm.train_dataset) == 18 and len(dm.eval_dataset) == 2
+    outs.save_dataparser_transform(tmp_path / "run" / "dataparser_transforms.json")
+    import json
+
+    j = json.loads((tmp_path / "run" / "dataparser_transforms.json").read_text())
+    assert j["scale"] == pytest.approx(scale) and np.allclose(j["transform"], transform.numpy())
+
+
+def test_dataparser_rejects_what_the_device_ray_generator_cannot_model(tmp_path):
+    from fruitnerf_b200.data.fruitnerf_dataparser import FruitNerf, FruitNerfDataParserConfig
+    import json
+
+    train, _ = make_apple_scene(num_images=10, height=8, width=8, num_fruits=2, seed=0, noise_std=0.0)
+    tj = write_dataset(train, tmp_path / "s")
+    meta = json.loads(tj.read_text())
+    meta["k1"] = 0.1
+    tj.write_text(json.dumps(meta))
+    with pytest.raises(NotImplementedError):
+        FruitNerf(FruitNerfDataParserConfig(data=tmp_path / "s")).get_dataparser_outputs("train")
+    meta["k1"] = 0.0
+    meta["train_filenames"] = ["images/frame_00000.png", "images/frame_00003.png"]
+    tj.write_text(json.dumps(meta))
+    out = FruitNerf(FruitNerfDataParserConfig(data=tj)).get_dataparser_outputs("train")  # explicit json path + split file list
+    assert len(out.image_filenames) == 2 and out.images.shape[0] == 2
+    with pytest.raises(RuntimeError):
+        FruitNerf(FruitNerfDataParserConfig(data=tj)).get_dataparser_outputs("val")
+
+
+def test_eval_setup_rebuilds_a_run_folder_on_cpu(tmp_path):
+    """config.yml + newest step-*.ckpt -> pipeline (scripts/exporter.py eval_setup; nerfstudio eval_utils.eval_setup)."""
+    import yaml
+
+    from fruitnerf_b200.scripts.exporter import eval_setup
+    from fruitnerf_b200.scripts.train import synthetic_spec
+
+    spec = synthetic_spec("fruit_nerf", num_images=10, image_size=16, num_fruits=2)
+    spec.pipeline.model.log2_hashmap_size = 10
+    pipe = spec.pipeline.setup(device="cpu", test_mode="val")
+    run = tmp_path / "outputs" / "exp" / "fruit_nerf" / "run0"
+    (run / "nerfstudio_models").mkdir(parents=True)
+    (run / "config.yml").write_text(yaml.dump(spec))
+    for step in (3, 12):
+        with torch.no_grad():
+            pipe.model.field.mlp_head.layers[0].bias.fill_(float(step))
+        torch.save({"step": step, "pipeline": pipe.state_dict()}, run / "nerfstudio_models" / f"step-{step:09d}.ckpt")
+    config, loaded, path, step = eval_setup(run / "config.yml", test_mode="export", device="cpu")
+    assert step == 12 and path.name == "step-000000012.ckpt" and not loaded.training
+    assert config.load_dir.parts[-3] == "fruit_nerf" and loaded.model.test_mode == "export"
+    a, b = pipe.state_dict(), loaded.state_dict()
+    assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
+    # reference-written checkpoints: upstream-only modules are dropped by the tolerant loader, strict loading refuses them
+    extra = dict(a)
+    extra["_model.lpips.net.weight"] = torch.zeros(3)
+    extra["datamanager.train_camera_optimizer.pose_adjustment"] = torch.zeros(5, 6)
+    with pytest.raises(RuntimeError):
+        loaded.load_pipeline(extra, 12)
+    loaded.load_pipeline({("module." + k): v for k, v in extra.items()}, 12, strict=False)
+    with pytest.raises(ValueError):
+        loaded.load_pipeline({**extra, "_model.field.mlp_base.params": torch.zeros(4)}, 12, strict=False)

@@ -8,7 +8,7 @@ from fruitnerf_b200.fruit_field import FruitField, SceneContraction
 from oracle import fruit_ref as fr
 
 REL = 1e-3  # north_star tolerance: 1e-3 relative on RGB / density / semantics
-FLOOR = 0.05  # elements below 5% of the tensor's max magnitude are compared absolutely
+FLOOR = 0.01  # elements below 1% of the tensor's max magnitude are compared absolutely (against rel * 1% * max)
 
 
 def assert_rel(actual, expected, rel=REL, floor=FLOOR, what=""):
