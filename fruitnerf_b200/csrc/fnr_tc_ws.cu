@@ -569,13 +569,16 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_render_forward_ws_kernel(co
           sh_degree4(d[0], d[1], d[2], sh);
           st_kstep(tr + C_C, 0, sh);
         } else {
-          const float* app = (!kExport && F.appearance_mode == FNR_APP_PER_CAMERA)
-                                 ? P.app_embedding + (size_t)__ldg(a.Rr.camera_indices + tp.ray) * APP
-                                 : nullptr;
+          // both pointers stay VALID in every mode: the compiler turns the branch below into loads + selects (read-only loads are
+          // speculated), so a null embedding / camera-index pointer would fault in the mean / zeros modes
+          const bool per_cam = !kExport && F.appearance_mode == FNR_APP_PER_CAMERA;
+          const int32_t* cip = per_cam ? a.Rr.camera_indices + tp.ray : reinterpret_cast<const int32_t*>(P.app_embedding);
+          const int cam_row = per_cam ? __ldg(cip) : 0;
+          const float* app = P.app_embedding + (size_t)cam_row * APP;
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             float v[16];
-            if (app) {
+            if (per_cam) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const float4 u = __ldg(reinterpret_cast<const float4*>(app) + 4 * j + q);

@@ -55,13 +55,14 @@ def test_whole_bench_batch_matches_oracle(native_lib, cuda_device, name):
         assert hi - lo == 1 and abs(float(cum[r, lo]) - 0.5) < 1e-5, f"median index mismatch on ray {r}"
 
 
-@pytest.mark.parametrize("name", ["small", "big"])
-def test_gradients_at_real_table_size_match_oracle(native_lib, cuda_device, name):
-    """fwd + bwd of 1024 rays x 192 samples through the tensor-core kernels at T = 19 (fruit_nerf) / 21 (fruit_nerf_big): every
-    MLP / head / embedding gradient element-wise and the hash-table gradient on EVERY row (dense comparison, most rows are zero on
-    both sides) at 2e-3 of the tensor scale.  Rays with a hidden unit within 1e-4 of a ReLU kink get zero loss weight on both
-    sides."""
-    R, S = 1024, 192
+@pytest.mark.parametrize("name,R,S", [("small", 4096, 48), ("big", 4096, 24)])
+def test_gradients_at_real_table_size_match_oracle(native_lib, cuda_device, name, R, S):
+    """fwd + bwd of 4096 rays through the tensor-core kernels at T = 19 (fruit_nerf) / 21 (fruit_nerf_big): every MLP / head /
+    embedding gradient element-wise and the hash-table gradient on EVERY row (dense comparison, most rows are zero on both sides)
+    at 2e-3 of the tensor scale.  Rays with a hidden unit within 1e-4 of a ReLU kink get zero loss weight on both sides
+    (DESIGN.md section 2); with 192 samples per ray almost no ray of random weights stays clear of every kink (measured: 48 /
+    1 of 1024), so the rays are shorter here -- the table size is the point of this test, the 192-sample shape is covered by
+    test_whole_bench_batch_matches_oracle."""
     sd, spec = make_state(name, table_scale=0.5)
     field = make_field(name, sd, spec, cuda_device).train()
     o, d, s, e, cam = syn.ray_batch(R, S, salt=3, num_images=7)
@@ -70,7 +71,7 @@ def test_gradients_at_real_table_size_match_oracle(native_lib, cuda_device, name
     sd_ref = {k: v.clone().requires_grad_(v.is_floating_point() and k != "aabb") for k, v in sd.items()}
     f, ref = _oracle(sd_ref, spec, o, d, s, e, cam)
     wr = (f["relu_margin"] > RELU_MARGIN).all(dim=1).float()[:, None]
-    assert wr.sum() >= 64, f"only {int(wr.sum())} of {R} rays keep a ReLU margin"
+    assert wr.sum() >= 256, f"only {int(wr.sum())} of {R} rays keep a ReLU margin"
     bce = torch.nn.functional.binary_cross_entropy_with_logits
 
     def loss_of(rgb, sem, w, image, m):
@@ -96,7 +97,7 @@ def test_gradients_at_real_table_size_match_oracle(native_lib, cuda_device, name
             touched = (g.cpu() != 0).any(dim=-1)
             # the same rows are touched (a row the oracle touches with an exactly-zero contribution may be skipped by the kernel)
             assert bool((touched & ~touched_ref).sum() == 0), "kernel wrote table rows the oracle does not touch"
-            assert int(touched_ref.sum()) > 100_000
+            assert int(touched_ref.sum()) > 50_000
         assert_rel(g, g_ref, rel=2e-3, floor=0.25, what=f"{name} grad {key}")
         checked += 1
     assert checked >= 14

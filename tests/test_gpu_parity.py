@@ -344,7 +344,9 @@ def test_export_with_stratified_jitter_matches_oracle(native_lib, cuda_device, n
     assert torch.equal(dense["point_location"].cpu(), ref["point_location"]), "jittered sample positions differ bitwise"
     assert not torch.equal(ref["point_location"], fr.export_outputs(sd, spec, o, dirs, nears, fars, n)["point_location"])
     assert_rel(dense["density"], ref["density"], what="density")
-    assert_rel(dense["semantics"], ref["semantics"], what="logit")
+    # logits of this deliberately large-weight field (weight_gain 2.5) are sums of terms ~100x the smallest |logit|: elements below
+    # 2% of the maximum are compared against 1e-3 * 2% * max (one of 9261 sits at 1.2e-5 of the maximum with the default 1% floor)
+    assert_rel(dense["semantics"], ref["semantics"], floor=0.02, what="logit")
     assert_rel(dense["rgb"], ref["rgb"], what="rgb")
     counts = buf.counts.cpu()
     keys = buf.keys[2][: int(counts[2])].cpu()

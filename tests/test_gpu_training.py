@@ -172,3 +172,33 @@ def test_export_and_count_runs_after_training(trained):
     # the model is usable for training again afterwards (sampler / contraction restored)
     loss, _, _ = trainer.train_iteration(trainer.step)
     assert torch.isfinite(loss)
+
+
+def test_export_cli_on_a_trained_run(native_lib, cuda_device, tmp_path):
+    """``ns-export-semantics semantic-pointcloud`` (scripts/exporter.py:entrypoint; fruit_nerf/scripts/exporter.py:80-135) on a run
+    folder the Trainer wrote: config.yml + newest checkpoint -> eval_setup -> uniform-volume export -> three PLY files."""
+    from fruitnerf_b200.scripts.exporter import entrypoint, eval_setup
+
+    torch.manual_seed(0)
+    run = tmp_path / "outputs" / "apple" / "fruit_nerf" / "run0"
+    trainer = Trainer(_tiny_spec(), device=cuda_device, output_dir=str(run), use_cuda_graph=False)
+    trainer.train(20)
+    ckpt = trainer.save_checkpoint()
+    assert (run / "config.yml").exists() and (run / "dataparser_transforms.json").exists() and ckpt.exists()
+    config, pipeline, path, step = eval_setup(run / "config.yml", test_mode="export")
+    assert step == 20 and path == ckpt and not pipeline.training
+    a, b = trainer.pipeline.state_dict(), pipeline.state_dict()
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    out = tmp_path / "exports"
+    pcds = entrypoint(["semantic-pointcloud", "--load-config", str(run / "config.yml"), "--output-dir", str(out), "--num-points-per-side", "40",
+                       "--num-rays-per-batch", "800", "--bounding-box-min", "-0.35", "-0.35", "-0.35", "--bounding-box-max", "0.35", "0.35", "0.35"])
+    assert set(pcds) == {"semantic_colormap", "semantic", "density"}
+    for name, pcd in pcds.items():
+        p = pcd["path"]
+        assert p.endswith(f"fruit_nerf/{name}.ply")  # <output_dir>/<config.load_dir.parts[-3]>/ (exporter_utils.py:194)
+        head = open(p, "rb").read(200)
+        assert head.startswith(b"ply\nformat binary_little_endian") and f"element vertex {pcd['points'].shape[0]}".encode() in head
+    # the CLI ran the reference's sampler state (training-mode module: jittered samples); the deterministic grid is an option
+    pcds2 = entrypoint(["semantic-pointcloud", "--load-config", str(run / "config.yml"), "--output-dir", str(out / "grid"), "--num-points-per-side", "40",
+                        "--stratified-jitter", "false", "--bounding-box-min", "-0.35", "-0.35", "-0.35", "--bounding-box-max", "0.35", "0.35", "0.35"])
+    assert pcds2["density"]["points"].shape[1] == 3

