@@ -96,11 +96,18 @@ struct ChainArgs {
   const float* point_grads;
   const float* stash;
   const float* sample_rgb;
+  float* denc;       // [N,32] encoding gradient for the level-major scatter of tc_big_dw_kernel, or NULL: scatter warps of this kernel
   uint8_t* records;  // scratch: ceil(N / 64) records of kRecBytes
   float* fold;       // [kFoldFloats] zero-initialised: the chain adds s = sum dlogit at [128]
   int debug_flags;   // FNR_DEBUG_BWD (timing experiments only): bit 0 skip the table scatter, bit 2 skip the X / dY stores
 };
 
+// 256-bit store (STG.E.ENL2.256): one whole 32-byte sector per lane and instruction; dst must be 32-byte aligned
+__device__ __forceinline__ void store8(float* dst, float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(a0), "f"(a1), "f"(a2), "f"(a3), "f"(a4), "f"(a5), "f"(a6),
+               "f"(a7)
+               : "memory");
+}
 // 16 values -> packed bf16 hi / lo words (two values per word)
 __device__ __forceinline__ void pack16(const float (&v)[16], uint32_t (&h)[8], uint32_t (&l)[8]) {
 #pragma unroll
@@ -156,6 +163,71 @@ __device__ __forceinline__ void issue_dx(uint32_t d_tmem, uint32_t a_tmem, uint3
     mma_ts(d_tmem, a_tmem + 8 * ks, wh, idesc, ks > 0);
     mma_ts(d_tmem, a_tmem + KR / 2 + 8 * ks, wh, idesc, true);
     mma_ts(d_tmem, a_tmem + 8 * ks, wl, idesc, true);
+  }
+}
+
+// ---- hash-table gradient of one level for a warp of points (lane = point; the 32 lanes are consecutive samples of a ray) ----
+// coarse levels: consecutive lanes share grid cells; a run of lanes in the same cell is summed with a segmented suffix scan and only
+// its head lane issues the 8 reds (run length ~25 at level 0, ~9 at level 3 on the bench batch)
+__device__ __forceinline__ void scatter_level_aggregated(float2* gtab, const Vec3& pos, bool live, float g0, float g1, int l, float scale, int log2T,
+                                                         uint32_t hmask, int lane) {
+  const LevelCell c = level_cell(pos, scale);
+  const uint32_t key = live ? (c.hx[0] ^ c.hy[0] ^ c.hz[0]) : (0x80000000u | (uint32_t)lane);
+  const uint32_t prev = __shfl_up_sync(kTcFullMask, key, 1);
+  const bool head = lane == 0 || prev != key;
+  const uint32_t heads = __ballot_sync(kTcFullMask, head);
+  const uint32_t above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
+  const int run_end = above ? (__ffs(above) - 1) : 32;
+  bool same[5];
+#pragma unroll
+  for (int q = 0; q < 5; ++q) same[q] = lane + (1 << q) < run_end;
+  if (!live) g0 = g1 = 0.f;
+  float v0[8], v1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float w = corner_weight(c, k);
+    v0[k] = w * g0;
+    v1[k] = w * g1;
+  }
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    const int dd = 1 << q;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float t0 = __shfl_down_sync(kTcFullMask, v0[k], dd), t1 = __shfl_down_sync(kTcFullMask, v1[k], dd);
+      if (same[q]) {
+        v0[k] += t0;
+        v1[k] += t1;
+      }
+    }
+  }
+  if (head && live) {
+    const uint32_t base = (uint32_t)l << log2T;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (v0[k] != 0.f || v1[k] != 0.f) atomicAdd(gtab + corner_row(c, k, hmask, base), make_float2(v0[k], v1[k]));
+  }
+}
+// fine levels: x-neighbours (floor x even, ceil = floor + 1) are adjacent table rows: one 16-byte red instead of two 8-byte ones
+__device__ __forceinline__ void scatter_level_direct(float2* gtab, const Vec3& pos, float g0, float g1, int l, float scale, int log2T, uint32_t hmask) {
+  if (g0 == 0.f && g1 == 0.f) return;
+  const LevelCell c = level_cell(pos, scale);
+  const uint32_t base = (uint32_t)l << log2T;
+  const bool pair = ((c.hx[0] & 1u) == 0u) && (c.hx[1] == c.hx[0] + 1u);
+  constexpr int kf[4] = {6, 7, 2, 3}, kc[4] = {5, 4, 1, 0};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float wf = corner_weight(c, kf[q]), wc = corner_weight(c, kc[q]);
+    const uint32_t rf = corner_row(c, kf[q], hmask, base);
+    if (pair) {
+      const uint32_t r0 = rf & ~1u;
+      const bool f_first = (rf & 1u) == 0u;
+      const float4 v = f_first ? make_float4(wf * g0, wf * g1, wc * g0, wc * g1) : make_float4(wc * g0, wc * g1, wf * g0, wf * g1);
+      atomicAdd(reinterpret_cast<float4*>(gtab + r0), v);
+    } else {
+      if (wf != 0.f) atomicAdd(gtab + rf, make_float2(wf * g0, wf * g1));
+      if (wc != 0.f) atomicAdd(gtab + corner_row(c, kc[q], hmask, base), make_float2(wc * g0, wc * g1));
+    }
   }
 }
 
@@ -247,6 +319,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
     // ================= scatter warps: hash-table gradient reds, decoupled from the tensor chain =================
     reg_dec<72>();
     const bool do_scatter = !(a.debug_flags & 1);
+    if (!a.denc) {  // (with a.denc the encoding gradient goes to global memory and tc_big_dw_kernel scatters it level by level)
     named_bar_arrive(BAR_EMPTY, kCtaThreads);
 #pragma unroll 1
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -263,80 +336,23 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
       const Vec3 pos = {pv.x, pv.y, pv.z};
       const bool live = pv.w != 0.f;
       if (do_scatter) {
-        // Levels 0..kAggLevels-1 (as in fnr_tc_bwd.cu): the 32 lanes of a warp are consecutive samples of a ray and share grid
-        // cells; a run of lanes in the same cell is summed with a segmented suffix scan and only its head lane issues the reds.
 #pragma unroll 1
         for (int l = 0; l < kAggLevels; ++l) {
-          const LevelCell c = level_cell(pos, F.scalings[l]);
-          const uint32_t key = live ? (c.hx[0] ^ c.hy[0] ^ c.hz[0]) : (0x80000000u | (uint32_t)lane);
-          const uint32_t prev = __shfl_up_sync(kTcFullMask, key, 1);
-          const bool head = lane == 0 || prev != key;
-          const uint32_t heads = __ballot_sync(kTcFullMask, head);
-          const uint32_t above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
-          const int run_end = above ? (__ffs(above) - 1) : 32;
-          bool same[5];
-#pragma unroll
-          for (int q = 0; q < 5; ++q) same[q] = lane + (1 << q) < run_end;
           float g0 = 0.f, g1 = 0.f;
 #pragma unroll
           for (int ll = 0; ll < kAggLevels; ++ll)
             if (ll == l) {
-              g0 = live ? g[2 * ll] : 0.f;
-              g1 = live ? g[2 * ll + 1] : 0.f;
+              g0 = g[2 * ll];
+              g1 = g[2 * ll + 1];
             }
-          float v0[8], v1[8];
+          scatter_level_aggregated(gtab, pos, live, g0, g1, l, F.scalings[l], F.log2T, hmask, lane);
+        }
+        if (live) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float w = corner_weight(c, k);
-            v0[k] = w * g0;
-            v1[k] = w * g1;
-          }
-#pragma unroll
-          for (int q = 0; q < 5; ++q) {
-            const int dd = 1 << q;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const float t0 = __shfl_down_sync(kTcFullMask, v0[k], dd), t1 = __shfl_down_sync(kTcFullMask, v1[k], dd);
-              if (same[q]) {
-                v0[k] += t0;
-                v1[k] += t1;
-              }
-            }
-          }
-          if (head && live) {
-            const uint32_t base = (uint32_t)l << F.log2T;
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              if (v0[k] != 0.f || v1[k] != 0.f) atomicAdd(gtab + corner_row(c, k, hmask, base), make_float2(v0[k], v1[k]));
-          }
+          for (int l = kAggLevels; l < 16; ++l) scatter_level_direct(gtab, pos, g[2 * l], g[2 * l + 1], l, F.scalings[l], F.log2T, hmask);
         }
       }
-      if (live && do_scatter) {
-#pragma unroll
-        for (int l = kAggLevels; l < 16; ++l) {
-          const float g0 = g[2 * l], g1 = g[2 * l + 1];
-          if (g0 != 0.f || g1 != 0.f) {
-            const LevelCell c = level_cell(pos, F.scalings[l]);
-            const uint32_t base = (uint32_t)l << F.log2T;
-            const bool pair = ((c.hx[0] & 1u) == 0u) && (c.hx[1] == c.hx[0] + 1u);  // x-neighbours: one 16-byte red
-            constexpr int kf[4] = {6, 7, 2, 3}, kc[4] = {5, 4, 1, 0};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float wf = corner_weight(c, kf[q]), wc = corner_weight(c, kc[q]);
-              const uint32_t rf = corner_row(c, kf[q], hmask, base);
-              if (pair) {
-                const uint32_t r0 = rf & ~1u;
-                const bool f_first = (rf & 1u) == 0u;
-                const float4 v = f_first ? make_float4(wf * g0, wf * g1, wc * g0, wc * g1) : make_float4(wc * g0, wc * g1, wf * g0, wf * g1);
-                atomicAdd(reinterpret_cast<float4*>(gtab + r0), v);
-              } else {
-                if (wf != 0.f) atomicAdd(gtab + rf, make_float2(wf * g0, wf * g1));
-                if (wc != 0.f) atomicAdd(gtab + corner_row(c, kc[q], hmask, base), make_float2(wc * g0, wc * g1));
-              }
-            }
-          }
-        }
-      }
+    }
     }
   } else {
   // ================= compute warps =================
@@ -658,14 +674,24 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
       uint32_t r[16];
       tmem_ld16(tr + R_D0 + 16 * half, r);
       tmem_ld_wait();
-      named_bar_sync(BAR_EMPTY, kCtaThreads);  // the scatter warps have copied the previous tile out
-      float4* dst = reinterpret_cast<float4*>(stage + row * STAGE_STRIDE + 16 * half);
+      if (a.denc) {
+        if (in_range) {
+          float* dst = a.denc + (size_t)p * ENC + 16 * half;  // 64-byte aligned: two whole sectors per thread
+          store8(dst, __uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]), __uint_as_float(r[4]),
+                 __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+          store8(dst + 8, __uint_as_float(r[8]), __uint_as_float(r[9]), __uint_as_float(r[10]), __uint_as_float(r[11]), __uint_as_float(r[12]),
+                 __uint_as_float(r[13]), __uint_as_float(r[14]), __uint_as_float(r[15]));
+        }
+      } else {
+        named_bar_sync(BAR_EMPTY, kCtaThreads);  // the scatter warps have copied the previous tile out
+        float4* dst = reinterpret_cast<float4*>(stage + row * STAGE_STRIDE + 16 * half);
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-      if (half == 0) reinterpret_cast<float4*>(stage + row * STAGE_STRIDE + 32)[0] = make_float4(pos.x, pos.y, pos.z, in_range ? 1.f : 0.f);
+        for (int q = 0; q < 4; ++q)
+          dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+        if (half == 0) reinterpret_cast<float4*>(stage + row * STAGE_STRIDE + 32)[0] = make_float4(pos.x, pos.y, pos.z, in_range ? 1.f : 0.f);
+      }
     }
-    named_bar_arrive(BAR_FULL, kCtaThreads);
+    if (!a.denc) named_bar_arrive(BAR_FULL, kCtaThreads);
     fence_before_sync();
   }
   // flush the running sums: warp reduce, one atomic per warp and value
@@ -694,7 +720,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
 // ======================================================================================================================
 // tc_big_dw_kernel: dW = dY^T X over all points, operands streamed by TMA, accumulators resident in tensor memory
 // ======================================================================================================================
-constexpr int kDwThreads = 256;   // warp 0: TMA producer, warp 1: MMA issue, all 8 warps: final flush
+constexpr int kDwThreads = 512;   // warp 0: TMA producer, warp 1: MMA issue, warps 2..15: level-major table scatter, warps 0..7: final flush
 constexpr int kDwSlots = 2;
 constexpr int DW_OFF_ONES = 0;                         // [2 chunks][64 points][16 B]: feature 0 = 1 (bias-gradient operand)
 constexpr int DW_OFF_RING = 2 * kChunk;
@@ -720,6 +746,11 @@ struct DwArgs {
   long long num_records;
   KParams G;
   float* fold;  // [kFoldFloats]: v[128] (+= over CTAs); [128] = s comes from the chain kernel
+  // level-major hash-table gradient scatter by the six otherwise idle warps (denc == NULL: the chain kernel scattered already)
+  const float* denc;  // [N,32]
+  KField F;
+  KRays Rr;
+  long long num_points;
 };
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -763,6 +794,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_big_dw_kernel(const __grid_c
     mbar_fence_init();
   }
   for (int i = tid; i < 2 * kRecPoints; i += kDwThreads)  // ONES: chunk 0 = (1, 0, 0, ...) per point, chunk 1 = 0
+    if (i < 2 * kRecPoints)
     *reinterpret_cast<uint4*>(smem + DW_OFF_ONES + i * 16) = make_uint4(i < kRecPoints ? 0x00003F80u : 0u, 0u, 0u, 0u);
   fence_async_smem();
   fence_before_sync();
@@ -832,8 +864,40 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_big_dw_kernel(const __grid_c
     __syncwarp();
   }
 
+  else if (a.denc) {
+    // ---- table scatter, LEVEL-MAJOR: all CTAs sweep level l together, so the reds of a sweep fall into ONE level's slice of the
+    // gradient table (2^T rows x 8 B = 16.8 MB at T = 21), which stays L2-resident -- scattered from inside the chain kernel, tile by
+    // tile over all 16 levels, they miss L2 (268 MB table) and every red is a DRAM read-modify-write.  This kernel's own work (a
+    // TMA-fed HBM stream + tensor-core MMAs issued by two threads) leaves the SM's LSU / atomic path idle: the two overlap.
+    const int sw = warp - 2;
+    constexpr int kSW = kDwThreads / 32 - 2;
+    const KField& F = a.F;
+    const uint32_t hmask = (1u << F.log2T) - 1u;
+    float2* const gtab = reinterpret_cast<float2*>(G.hash_table);
+    const long long N = a.num_points;
+    const long long chunks = (N + 31) / 32;
+    const int S = a.Rr.S;
+#pragma unroll 1
+    for (int l = 0; l < F.L; ++l) {
+      const float scale = F.scalings[l];
+#pragma unroll 1
+      for (long long c = (long long)blockIdx.x * kSW + sw; c < chunks; c += (long long)gridDim.x * kSW) {
+        const long long p = c * 32 + lane;
+        const bool live = p < N;
+        const long long pc = live ? p : N - 1;
+        const int ray = (int)(pc / S);
+        bool sel;
+        const Vec3 pos = field_position(a.Rr.origins + 3 * (size_t)ray, a.Rr.directions + 3 * (size_t)ray, __ldg(a.Rr.starts + pc),
+                                        __ldg(a.Rr.ends + pc), F.position_mode, F.aabb, sel);
+        const float2 g = __ldg(reinterpret_cast<const float2*>(a.denc + (size_t)pc * ENC) + l);
+        if (l < kAggLevels) scatter_level_aggregated(gtab, pos, live, g.x, g.y, l, scale, F.log2T, hmask, lane);
+        else if (live) scatter_level_direct(gtab, pos, g.x, g.y, l, scale, F.log2T, hmask);
+      }
+    }
+  }
+
   // ---- flush: every accumulator once per CTA, atomics into the torch-layout gradient tensors
-  if (my_records > 0) {
+  if (my_records > 0 && warp < 8) {
     mbar_wait(&s_done, 0);
     fence_after_sync();
     const int quarter = warp & 3, half = warp >> 2;  // 8 warps: lane quarter x column half
@@ -959,7 +1023,7 @@ __global__ void __launch_bounds__(256) big_fold_kernel(const float* __restrict__
 
 size_t tc_big_backward_scratch_bytes(long long num_points) {
   const long long records = 2 * ((num_points + 127) / 128);
-  return (size_t)records * kRecBytes + (size_t)kFoldFloats * sizeof(float) + 4096;
+  return (size_t)records * kRecBytes + (size_t)num_points * ENC * sizeof(float) + (size_t)kFoldFloats * sizeof(float) + 8192;
 }
 
 bool tc_big_backward_supported(const KField& F, const KFieldBwd& B) {
@@ -998,6 +1062,9 @@ int launch_tc_big_field_backward(const KField& F, const KParams& P, const KParam
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(Bw.extra) + 255) & ~(uintptr_t)255);
   a.fold = reinterpret_cast<float*>(base);
   a.records = base + 1024;
+  // FNR_BIG_BWD_MODE=0: round-1 placement of the table scatter (scatter warps inside the chain kernel), for A/B timing
+  static const bool level_major = !(getenv("FNR_BIG_BWD_MODE") && atoi(getenv("FNR_BIG_BWD_MODE")) == 0);
+  a.denc = level_major ? reinterpret_cast<float*>(base + 1024 + (size_t)(2 * tiles) * kRecBytes) : nullptr;
   if (int rc = check_cuda(cudaMemsetAsync(a.fold, 0, kFoldFloats * sizeof(float), st), "cudaMemsetAsync(fold)")) return rc;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   tc_big_backward_chain_kernel<<<grid, kCtaThreads, kSmemBytes, st>>>(a);
@@ -1009,6 +1076,10 @@ int launch_tc_big_field_backward(const KField& F, const KParams& P, const KParam
   d.num_records = 2 * tiles;
   d.G = G;
   d.fold = a.fold;
+  d.denc = (a.debug_flags & 1) ? nullptr : a.denc;
+  d.F = F;
+  d.Rr = Rr;
+  d.num_points = N;
   const int dgrid = (int)(d.num_records < sm_count() ? d.num_records : sm_count());
   tc_big_dw_kernel<<<dgrid, kDwThreads, kDwSmem, st>>>(d);
   if (int rc = check_launch("tc_big_dw_kernel")) return rc;

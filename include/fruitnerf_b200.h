@@ -331,7 +331,7 @@ typedef struct fnr_nvls_desc {
   void* grid_counter;                /* device uint32, zero before the first call (wire_bf16 only), or NULL */
   int32_t rank, world_size;
   int32_t signal_slots;              /* uint32 slots in each pad */
-  int32_t signal_slot_base;          /* first slot this library may use (64 blocks x world_size slots from there) */
+  int32_t signal_slot_base;          /* first slot this library may use (up to 144 blocks x world_size slots from there) */
 } fnr_nvls_desc;
 
 /* In place: region[i] = mean over ranks of region[i], i < numel (numel % (8 * world_size) == 0).  Every rank calls it with
