@@ -166,71 +166,6 @@ __device__ __forceinline__ void issue_dx(uint32_t d_tmem, uint32_t a_tmem, uint3
   }
 }
 
-// ---- hash-table gradient of one level for a warp of points (lane = point; the 32 lanes are consecutive samples of a ray) ----
-// coarse levels: consecutive lanes share grid cells; a run of lanes in the same cell is summed with a segmented suffix scan and only
-// its head lane issues the 8 reds (run length ~25 at level 0, ~9 at level 3 on the bench batch)
-__device__ __forceinline__ void scatter_level_aggregated(float2* gtab, const Vec3& pos, bool live, float g0, float g1, int l, float scale, int log2T,
-                                                         uint32_t hmask, int lane) {
-  const LevelCell c = level_cell(pos, scale);
-  const uint32_t key = live ? (c.hx[0] ^ c.hy[0] ^ c.hz[0]) : (0x80000000u | (uint32_t)lane);
-  const uint32_t prev = __shfl_up_sync(kTcFullMask, key, 1);
-  const bool head = lane == 0 || prev != key;
-  const uint32_t heads = __ballot_sync(kTcFullMask, head);
-  const uint32_t above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
-  const int run_end = above ? (__ffs(above) - 1) : 32;
-  bool same[5];
-#pragma unroll
-  for (int q = 0; q < 5; ++q) same[q] = lane + (1 << q) < run_end;
-  if (!live) g0 = g1 = 0.f;
-  float v0[8], v1[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const float w = corner_weight(c, k);
-    v0[k] = w * g0;
-    v1[k] = w * g1;
-  }
-#pragma unroll
-  for (int q = 0; q < 5; ++q) {
-    const int dd = 1 << q;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float t0 = __shfl_down_sync(kTcFullMask, v0[k], dd), t1 = __shfl_down_sync(kTcFullMask, v1[k], dd);
-      if (same[q]) {
-        v0[k] += t0;
-        v1[k] += t1;
-      }
-    }
-  }
-  if (head && live) {
-    const uint32_t base = (uint32_t)l << log2T;
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (v0[k] != 0.f || v1[k] != 0.f) atomicAdd(gtab + corner_row(c, k, hmask, base), make_float2(v0[k], v1[k]));
-  }
-}
-// fine levels: x-neighbours (floor x even, ceil = floor + 1) are adjacent table rows: one 16-byte red instead of two 8-byte ones
-__device__ __forceinline__ void scatter_level_direct(float2* gtab, const Vec3& pos, float g0, float g1, int l, float scale, int log2T, uint32_t hmask) {
-  if (g0 == 0.f && g1 == 0.f) return;
-  const LevelCell c = level_cell(pos, scale);
-  const uint32_t base = (uint32_t)l << log2T;
-  const bool pair = ((c.hx[0] & 1u) == 0u) && (c.hx[1] == c.hx[0] + 1u);
-  constexpr int kf[4] = {6, 7, 2, 3}, kc[4] = {5, 4, 1, 0};
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float wf = corner_weight(c, kf[q]), wc = corner_weight(c, kc[q]);
-    const uint32_t rf = corner_row(c, kf[q], hmask, base);
-    if (pair) {
-      const uint32_t r0 = rf & ~1u;
-      const bool f_first = (rf & 1u) == 0u;
-      const float4 v = f_first ? make_float4(wf * g0, wf * g1, wc * g0, wc * g1) : make_float4(wc * g0, wc * g1, wf * g0, wf * g1);
-      atomicAdd(reinterpret_cast<float4*>(gtab + r0), v);
-    } else {
-      if (wf != 0.f) atomicAdd(gtab + rf, make_float2(wf * g0, wf * g1));
-      if (wc != 0.f) atomicAdd(gtab + corner_row(c, kc[q], hmask, base), make_float2(wc * g0, wc * g1));
-    }
-  }
-}
-
 __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(const __grid_constant__ ChainArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -722,6 +657,11 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
 // ======================================================================================================================
 constexpr int kDwThreads = 512;   // warp 0: TMA producer, warp 1: MMA issue, warps 2..15: level-major table scatter, warps 0..7: final flush
 constexpr int kDwSlots = 2;
+#ifndef FNR_DW_AGG_LEVELS
+#define FNR_DW_AGG_LEVELS 9
+#endif
+constexpr int kDwAggLevels = FNR_DW_AGG_LEVELS;  // levels whose reds are run-length merged across the warp in the level-major scatter: the reds are bound by
+                                                 // the chip-wide L2 atomic request rate (~65-80 G requests/s measured), the SMs of this kernel are otherwise idle
 constexpr int DW_OFF_ONES = 0;                         // [2 chunks][64 points][16 B]: feature 0 = 1 (bias-gradient operand)
 constexpr int DW_OFF_RING = 2 * kChunk;
 constexpr int kDwSmem = DW_OFF_RING + kDwSlots * kStageMax + 1024;
@@ -890,7 +830,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_big_dw_kernel(const __grid_c
         const Vec3 pos = field_position(a.Rr.origins + 3 * (size_t)ray, a.Rr.directions + 3 * (size_t)ray, __ldg(a.Rr.starts + pc),
                                         __ldg(a.Rr.ends + pc), F.position_mode, F.aabb, sel);
         const float2 g = __ldg(reinterpret_cast<const float2*>(a.denc + (size_t)pc * ENC) + l);
-        if (l < kAggLevels) scatter_level_aggregated(gtab, pos, live, g.x, g.y, l, scale, F.log2T, hmask, lane);
+        if (l < kDwAggLevels) scatter_level_aggregated(gtab, pos, live, g.x, g.y, l, scale, F.log2T, hmask, lane);
         else if (live) scatter_level_direct(gtab, pos, g.x, g.y, l, scale, F.log2T, hmask);
       }
     }

@@ -74,5 +74,85 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 }
 
 
+// ---- hash-table gradient of one level for a warp of points (lane = point; the 32 lanes are consecutive samples of a ray) ----------
+// Coarse / middle levels: consecutive lanes share grid cells.  A run of lanes in the same cell is summed with a segmented suffix scan
+// and only its head lane issues the reds (run length ~25 at level 0, ~9 at level 3, ~2 at level 8 on the bench batch); x-neighbour
+// corners go out as one 16-byte red when they are adjacent table rows.  Reds are bound by the chip-wide L2 atomic REQUEST rate, so a
+// merged run saves its requests whatever its width.
+__device__ __forceinline__ void scatter_level_aggregated(float2* gtab, const Vec3& pos, bool live, float g0, float g1, int l, float scale, int log2T,
+                                                         uint32_t hmask, int lane) {
+  const LevelCell c = level_cell(pos, scale);
+  const uint32_t key = live ? (c.hx[0] ^ c.hy[0] ^ c.hz[0]) : (0x80000000u | (uint32_t)lane);
+  const uint32_t prev = __shfl_up_sync(kTcFullMask, key, 1);
+  const bool head = lane == 0 || prev != key;
+  const uint32_t heads = __ballot_sync(kTcFullMask, head);
+  const uint32_t above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
+  const int run_end = above ? (__ffs(above) - 1) : 32;
+  bool same[5];
+#pragma unroll
+  for (int q = 0; q < 5; ++q) same[q] = lane + (1 << q) < run_end;
+  if (!live) g0 = g1 = 0.f;
+  float v0[8], v1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float w = corner_weight(c, k);
+    v0[k] = w * g0;
+    v1[k] = w * g1;
+  }
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    const int dd = 1 << q;
+    if (__any_sync(kTcFullMask, same[q])) {  // warp-uniform: skip the steps no run in this warp is long enough for
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float t0 = __shfl_down_sync(kTcFullMask, v0[k], dd), t1 = __shfl_down_sync(kTcFullMask, v1[k], dd);
+        if (same[q]) {
+          v0[k] += t0;
+          v1[k] += t1;
+        }
+      }
+    }
+  }
+  if (head && live) {
+    const uint32_t base = (uint32_t)l << log2T;
+    const bool pair = ((c.hx[0] & 1u) == 0u) && (c.hx[1] == c.hx[0] + 1u);
+    constexpr int kf[4] = {6, 7, 2, 3}, kc[4] = {5, 4, 1, 0};  // corner pairs (x floor, x ceil) per (y, z)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t rf = corner_row(c, kf[q], hmask, base);
+      if (pair) {
+        const bool f_first = (rf & 1u) == 0u;
+        const float4 v = f_first ? make_float4(v0[kf[q]], v1[kf[q]], v0[kc[q]], v1[kc[q]]) : make_float4(v0[kc[q]], v1[kc[q]], v0[kf[q]], v1[kf[q]]);
+        if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) atomicAdd(reinterpret_cast<float4*>(gtab + (rf & ~1u)), v);
+      } else {
+        if (v0[kf[q]] != 0.f || v1[kf[q]] != 0.f) atomicAdd(gtab + rf, make_float2(v0[kf[q]], v1[kf[q]]));
+        if (v0[kc[q]] != 0.f || v1[kc[q]] != 0.f) atomicAdd(gtab + corner_row(c, kc[q], hmask, base), make_float2(v0[kc[q]], v1[kc[q]]));
+      }
+    }
+  }
+}
+// fine levels: x-neighbours (floor x even, ceil = floor + 1) are adjacent table rows: one 16-byte red instead of two 8-byte ones
+__device__ __forceinline__ void scatter_level_direct(float2* gtab, const Vec3& pos, float g0, float g1, int l, float scale, int log2T, uint32_t hmask) {
+  if (g0 == 0.f && g1 == 0.f) return;
+  const LevelCell c = level_cell(pos, scale);
+  const uint32_t base = (uint32_t)l << log2T;
+  const bool pair = ((c.hx[0] & 1u) == 0u) && (c.hx[1] == c.hx[0] + 1u);
+  constexpr int kf[4] = {6, 7, 2, 3}, kc[4] = {5, 4, 1, 0};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float wf = corner_weight(c, kf[q]), wc = corner_weight(c, kc[q]);
+    const uint32_t rf = corner_row(c, kf[q], hmask, base);
+    if (pair) {
+      const uint32_t r0 = rf & ~1u;
+      const bool f_first = (rf & 1u) == 0u;
+      const float4 v = f_first ? make_float4(wf * g0, wf * g1, wc * g0, wc * g1) : make_float4(wc * g0, wc * g1, wf * g0, wf * g1);
+      atomicAdd(reinterpret_cast<float4*>(gtab + r0), v);
+    } else {
+      if (wf != 0.f) atomicAdd(gtab + rf, make_float2(wf * g0, wf * g1));
+      if (wc != 0.f) atomicAdd(gtab + corner_row(c, kc[q], hmask, base), make_float2(wc * g0, wc * g1));
+    }
+  }
+}
+
 }  // namespace tcx
 }  // namespace fnr
