@@ -19,6 +19,9 @@ import torch
 import torch.distributed as dist
 
 
+NVLS_AUTO_MIN_WORLD = 4  # "auto" uses the multimem kernel from this world size on
+
+
 class GradientExchange:
     def __init__(self, flat: torch.Tensor, world: int, kind: str, note: str = ""):
         self.flat, self.world, self.kind, self.note = flat, world, kind, note
@@ -44,6 +47,9 @@ def make_gradient_exchange(numel: int, world: int, device, kind: str = "auto") -
         return None
     device = torch.device(device)
     note = ""
+    if kind == "auto" and world < NVLS_AUTO_MIN_WORLD:
+        kind = "nccl"  # measured at N = 2 (tools/r2/nvls_test.py): NCCL 154 us vs 201-213 us for 67 MB -- with two ranks in-switch reduction moves
+                       # MORE bytes per GPU than a direct exchange (every operand, the local one included, travels to the switch)
     if kind in ("auto", "nvls", "nvls_bf16") and device.type == "cuda":
         try:
             from .nvls import NvlsExchange

@@ -1,0 +1,17 @@
+#!/bin/bash
+# N = 8 rehearsal of the driver's scaling bench: NVLS kernel vs NCCL on the two flat-gradient sizes, then bench.py with both exchanges
+mkdir -p gpurun_out
+R="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
+timeout -k 10 150 $R --master-port 29511 tools/r2/nvls_test.py > gpurun_out/r2_nvls_test_n8.log 2>&1; echo "nvls test rc=$?"; grep "^nccl\|^nvls" gpurun_out/r2_nvls_test_n8.log | cut -c1-150
+for ex in nccl nvls; do
+  timeout -k 10 200 $R --master-port 29512 bench.py --gpus 8 --steps 20 --warmup 3 --exchange $ex > gpurun_out/r2_bench_n8_$ex.json 2> gpurun_out/r2_bench_n8_$ex.err; echo "bench $ex rc=$?"
+  python - <<PY
+import json
+try:
+    j=json.loads(open('gpurun_out/r2_bench_n8_$ex.json').read().strip().splitlines()[-1])
+    b=j.get('variants',{}).get('big',{})
+    print('$ex', {k:round(j[k],4) for k in ('value','ms_per_step','comm_ms')}, j.get('exchange',{}).get('kind'), 'big', {k:round(b[k],4) for k in ('value','ms_per_step','comm_ms') if k in b}, b.get('exchange',{}).get('kind'), b.get('error'))
+except Exception as e:
+    print('$ex parse failed', e); print(open('gpurun_out/r2_bench_n8_$ex.err').read()[-1500:])
+PY
+done
