@@ -30,7 +30,13 @@ using namespace tcx;
 namespace {
 
 constexpr int kTC = 256;  // compute threads: 2 threads per point (column halves), 8 warps
-constexpr int kTS = 128;  // scatter threads: 4 warps that only issue the hash-table gradient reds
+#ifndef FNR_BWD_SCATTER_WARPS
+#define FNR_BWD_SCATTER_WARPS 4
+#endif
+constexpr int kScatterWarps = FNR_BWD_SCATTER_WARPS;  // 4: one thread per point, all 16 levels; 8: two threads per point, 8 levels each
+constexpr int kTS = 32 * kScatterWarps;  // scatter threads: warps that only issue the hash-table gradient reds
+constexpr int kComputeRegs = kScatterWarps == 4 ? 216 : 184;
+static_assert(kScatterWarps == 4 || kScatterWarps == 8, "scatter warps");
 constexpr int kT = kTC + kTS;
 constexpr int GEO = 15, ENC = 32, H = 64, APP = 32, SHD = 16;
 
@@ -303,7 +309,9 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
       if (tile + gridDim.x < tiles) named_bar_arrive(BAR_EMPTY, kT);  // staging may be overwritten
       const Vec3 pos = {pv.x, pv.y, pv.z};
       const bool live = pv.w != 0.f;
-      if (do_scatter) {
+      // 8 scatter warps: warps 0-3 take levels 0-7 of their point, warps 4-7 levels 8-15
+      const int lsplit = kScatterWarps == 8 ? ((tid - kTC) >> 7) : 0;
+      if (do_scatter && lsplit == 0) {
         // Levels 0..kAggLevels-1: the 32 lanes of a warp are consecutive samples of a ray and share grid cells, so the
         // contributions of a run of lanes in the same cell are summed with a segmented suffix scan and only
         // the head lane of each run issues the 8 reds (run length ~25 at level 0, ~2.6 at level 7 on the
@@ -348,11 +356,13 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
               if (v0[k] != 0.f || v1[k] != 0.f) atomicAdd(gtab + corner_row(c, k, hmask, base), make_float2(v0[k], v1[k]));
           }
         }
+      }
+      if (do_scatter) {
         if (live) {
 #pragma unroll
           for (int l = kAggLevels; l < 16; ++l) {
             const float g0 = g[2 * l], g1 = g[2 * l + 1];
-            if (g0 != 0.f || g1 != 0.f) {
+            if ((kScatterWarps == 4 || (l < 8) == (lsplit == 0)) && (g0 != 0.f || g1 != 0.f)) {
               const LevelCell c = level_cell(pos, F.scalings[l]);
               const uint32_t base = (uint32_t)l << F.log2T;
               // x-neighbours (floor x even, ceil = floor + 1) are adjacent table rows r, r^1: one 16-byte red
@@ -380,7 +390,7 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
     }
   } else {
   // ================= compute warps: recompute + dX / dW chain on the tensor cores =================
-  reg_inc<216>();
+  reg_inc<kComputeRegs>();
 #pragma unroll 1
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const long long p = tile * 128 + row;

@@ -108,6 +108,25 @@ class GraphedTrainStep:
         torch.cuda.current_stream(self.device).wait_event(self._copy_done)
         self._flat.copy_(self._staging, non_blocking=True)
 
+    # ---- result read-back ----------------------------------------------------------------------------
+    def read_loss_async(self):
+        """Start the device->host copy of the current step's loss into pinned memory; returns a handle whose ``value()``
+        waits for that copy only (not for later work) -- the way a training loop logs its loss without draining the GPU."""
+        if not hasattr(self, "_loss_ring"):
+            self._loss_ring = [(torch.zeros(1).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+            self._loss_next = 0
+        buf, ev = self._loss_ring[self._loss_next]
+        self._loss_next = (self._loss_next + 1) % len(self._loss_ring)
+        buf.copy_(self.loss.reshape(1), non_blocking=True)
+        ev.record(torch.cuda.current_stream(self.device))
+
+        class _Handle:
+            def value(self_inner) -> float:
+                ev.synchronize()
+                return float(buf[0])
+
+        return _Handle()
+
     # ---- the step ---------------------------------------------------------------------------------
     def _eager(self) -> Tensor:
         f, st = self.field, self.static

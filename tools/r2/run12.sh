@@ -1,0 +1,16 @@
+#!/bin/bash
+mkdir -p gpurun_out
+T="timeout -s KILL"
+for v in default sw8; do
+  if [ "$v" = default ]; then unset FNR_LIB; else export FNR_LIB=$PWD/tools/bin/libfnr_$v.so; fi
+  $T 100 python bench.py --steps 20 --warmup 3 --no-cpu --no-train --no-variants > gpurun_out/r2_bench_$v.json 2> gpurun_out/r2_bench_$v.err; rc=$?
+  python - <<PY
+import json
+try:
+    j=json.loads(open('gpurun_out/r2_bench_$v.json').read())
+    print('small $v rc=$rc', {k:round(j[k],4) for k in ('value','ms_per_step','fwd_ms','bwd_ms')}, 'e2e', int(j['e2e']['value']))
+except Exception as e:
+    print('$v rc=$rc parse failed', e); print(open('gpurun_out/r2_bench_$v.err').read()[-600:])
+PY
+done
+FNR_LIB=$PWD/tools/bin/libfnr_sw8.so $T 200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -m gpu -x -q --timeout 120 -k "(backward or gradients) and small" > gpurun_out/r2_pytest_sw8.log 2>&1; echo "sw8 parity rc=$?"; tail -2 gpurun_out/r2_pytest_sw8.log | cut -c1-300
