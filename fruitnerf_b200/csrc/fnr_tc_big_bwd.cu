@@ -830,6 +830,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_big_dw_kernel(const __grid_c
         const Vec3 pos = field_position(a.Rr.origins + 3 * (size_t)ray, a.Rr.directions + 3 * (size_t)ray, __ldg(a.Rr.starts + pc),
                                         __ldg(a.Rr.ends + pc), F.position_mode, F.aabb, sel);
         const float2 g = __ldg(reinterpret_cast<const float2*>(a.denc + (size_t)pc * ENC) + l);
+        // full segmented scan here (the 14 scatter warps of this kernel hide its shuffles; the one-round merge the small backward
+        // uses measured 2.34 ms against 2.13 ms for the backward phase, no merge 2.52 ms -- tools/r2/run18.sh)
         if (l < kDwAggLevels) scatter_level_aggregated(gtab, pos, live, g.x, g.y, l, scale, F.log2T, hmask, lane);
         else if (live) scatter_level_direct(gtab, pos, g.x, g.y, l, scale, F.log2T, hmask);
       }

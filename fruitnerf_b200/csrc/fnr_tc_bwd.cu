@@ -18,6 +18,7 @@
 // semantic branch is chunks 6-7 of the colour-input tile, so no activation is stored twice.
 // Bias gradients come for free from constant-1 columns (padding columns of the geo / colour-input tiles,
 // a 128x16 ONES tile for the K-exact layers) or from per-thread running sums (3- and 16-wide layers).
+#include <cstdio>
 #include <cstdlib>
 #include "fnr_common.cuh"
 #include "fnr_kernels.h"
@@ -35,9 +36,11 @@ constexpr int kTC = 256;  // compute threads: 2 threads per point (column halves
 #endif
 constexpr int kScatterWarps = FNR_BWD_SCATTER_WARPS;  // 4: one thread per point, all 16 levels; 8: two threads per point, 8 levels each
 constexpr int kTS = 32 * kScatterWarps;  // scatter threads: warps that only issue the hash-table gradient reds
+constexpr int kScatterRegs = 72;  // setmaxnreg budgets: kTS * kScatterRegs + kTC * kComputeRegs <= 64 K registers
 constexpr int kComputeRegs = kScatterWarps == 4 ? 216 : 184;
 static_assert(kScatterWarps == 4 || kScatterWarps == 8, "scatter warps");
 constexpr int kT = kTC + kTS;
+static_assert(kTS * kScatterRegs + kTC * kComputeRegs <= 65536 && kScatterRegs % 8 == 0 && kComputeRegs % 8 == 0, "register budget");
 constexpr int GEO = 15, ENC = 32, H = 64, APP = 32, SHD = 16;
 
 // ---- shared-memory map (bytes) ------------------------------------------------------------------
@@ -171,10 +174,13 @@ __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.al
 template <int N>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 constexpr int BAR_COMPUTE = 1, BAR_FULL = 2, BAR_EMPTY = 3;
-#ifndef FNR_AGG_LEVELS
-#define FNR_AGG_LEVELS 4
+#ifndef FNR_MERGE_END
+#define FNR_MERGE_END 8
 #endif
-constexpr int kAggLevels = FNR_AGG_LEVELS;  // coarse levels whose reds are run-length aggregated across the warp
+// Levels 0 .. kMergeEnd-1 of the table-gradient scatter merge neighbouring lanes of a same-cell run before issuing (see the scatter
+// warps below); measured on the bench batch (tools/r2/run16.sh, run17.sh): no merge on the coarse levels 0.91 ms, the round-1 full
+// segmented scan (5 shuffle rounds) on levels 0-3 0.843 ms, one round on levels 0-5 / 0-7 / 0-15 0.814 ms.
+constexpr int kMergeEnd = FNR_MERGE_END;
 
 struct BwdArgs {
   KField F;
@@ -270,10 +276,22 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
   float acc_dlogit = 0.f;
   bool first = true;
 
+#ifdef FNR_BWD_PROF  // role timers of CTA 0 (experiment builds only: tools/r2/build_variant.sh prof fnr_tc_bwd.cu -DFNR_BWD_PROF)
+  const bool prof = blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == 8);
+  long long t_mark = 0, t_total = clock64(), t_epi = 0, t_bar = 0, t_wait[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_empty = 0, t_full = 0, t_agg = 0, t_direct = 0;
+  int wait_idx = 0, n_tiles = 0;
+#define PROF_MARK() if (prof) t_mark = clock64();
+#define PROF_ADD(x) if (prof) { const long long t_now = clock64(); x += t_now - t_mark; t_mark = t_now; }
+#else
+#define PROF_MARK()
+#define PROF_ADD(x)
+#endif
 #define FNR_SYNC_ISSUE(...)            \
   fence_async_smem();                  \
   fence_before_sync();                 \
+  PROF_ADD(t_epi)                      \
   named_bar_sync(BAR_COMPUTE, kTC);    \
+  PROF_ADD(t_bar)                      \
   if (warp == 0) {                     \
     if (elect_one_sync()) {            \
       fence_after_sync();              \
@@ -283,21 +301,31 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
     __syncwarp();                      \
   }
 #define FNR_WAIT()          \
+  PROF_ADD(t_epi)           \
   mbar_wait(&s_bar, phase); \
   phase ^= 1;               \
-  fence_after_sync();
+  fence_after_sync();       \
+  PROF_ADD(t_wait[wait_idx]) \
+  PROF_WAIT_NEXT()
+#ifdef FNR_BWD_PROF
+#define PROF_WAIT_NEXT() wait_idx = wait_idx == 8 ? 0 : wait_idx + 1;
+#else
+#define PROF_WAIT_NEXT()
+#endif
 
   float* stage = reinterpret_cast<float*>(tC1);  // [128][STAGE_STRIDE]: denc[32], pos xyz, valid (see STAGE_STRIDE)
 
   if (!is_compute) {
     // ================= scatter warps: hash-table gradient reds, decoupled from the tensor chain =================
-    reg_dec<72>();
+    reg_dec<kScatterRegs>();
     float2* const gtab = reinterpret_cast<float2*>(G.hash_table);
     const bool do_scatter = !(a.debug_flags & 1);
     named_bar_arrive(BAR_EMPTY, kT);
 #pragma unroll 1
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      PROF_MARK()
       named_bar_sync(BAR_FULL, kT);
+      PROF_ADD(t_full)
       float g[32];
       const float4* src = reinterpret_cast<const float4*>(stage + row * STAGE_STRIDE);
 #pragma unroll
@@ -311,56 +339,21 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
       const bool live = pv.w != 0.f;
       // 8 scatter warps: warps 0-3 take levels 0-7 of their point, warps 4-7 levels 8-15
       const int lsplit = kScatterWarps == 8 ? ((tid - kTC) >> 7) : 0;
+      // Levels 0 .. kMergeEnd-1: the 32 lanes of a warp are consecutive samples of a ray and share grid cells (run length ~25 at
+      // level 0, ~2.6 at level 7 on the bench workload).  ONE shuffle round: the lane at an even position of a run of same-cell
+      // lanes absorbs its successor (16 shuffles), which halves the red lanes of these levels.  The full segmented scan of
+      // round 1 (5 rounds, 80 shuffles per level, one issuing lane per run) was slower: every shuffle and every red of these
+      // warps goes through the SM's one memory-instruction queue, so it is instructions, not lanes, that have to be saved
+      // (profiles/r2_red_probe.log, profiles/r2_backward_experiments.md).
       if (do_scatter && lsplit == 0) {
-        // Levels 0..kAggLevels-1: the 32 lanes of a warp are consecutive samples of a ray and share grid cells, so the
-        // contributions of a run of lanes in the same cell are summed with a segmented suffix scan and only
-        // the head lane of each run issues the 8 reds (run length ~25 at level 0, ~2.6 at level 7 on the
-        // bench workload).  The SM sustains only ~0.4 scattered 8-byte red lanes per cycle: fewer lanes = faster.
 #pragma unroll 1
-        for (int l = 0; l < kAggLevels; ++l) {
-          const LevelCell c = level_cell(pos, F.scalings[l]);
-          const uint32_t key = live ? (c.hx[0] ^ c.hy[0] ^ c.hz[0]) : (0x80000000u | (uint32_t)lane);
-          const uint32_t prev = __shfl_up_sync(kTcFullMask, key, 1);
-          const bool head = lane == 0 || prev != key;
-          // run = maximal stretch of CONSECUTIVE lanes with the same cell: [lane, run_end)
-          const uint32_t heads = __ballot_sync(kTcFullMask, head);
-          const uint32_t above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
-          const int run_end = above ? (__ffs(above) - 1) : 32;
-          bool same[5];
-#pragma unroll
-          for (int q = 0; q < 5; ++q) same[q] = lane + (1 << q) < run_end;
-          const float g0 = live ? g[2 * l] : 0.f, g1 = live ? g[2 * l + 1] : 0.f;
-          float v0[8], v1[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float w = corner_weight(c, k);
-            v0[k] = w * g0;
-            v1[k] = w * g1;
-          }
-#pragma unroll
-          for (int q = 0; q < 5; ++q) {
-            const int dd = 1 << q;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const float t0 = __shfl_down_sync(kTcFullMask, v0[k], dd), t1 = __shfl_down_sync(kTcFullMask, v1[k], dd);
-              if (same[q]) {
-                v0[k] += t0;
-                v1[k] += t1;
-              }
-            }
-          }
-          if (head && live) {
-            const uint32_t base = (uint32_t)l << F.log2T;
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              if (v0[k] != 0.f || v1[k] != 0.f) atomicAdd(gtab + corner_row(c, k, hmask, base), make_float2(v0[k], v1[k]));
-          }
-        }
+        for (int l = 0; l < kMergeEnd; ++l) scatter_level_merged1(gtab, pos, live, g[2 * l], g[2 * l + 1], l, F.scalings[l], F.log2T, hmask, lane);
       }
+      PROF_ADD(t_agg)
       if (do_scatter) {
         if (live) {
 #pragma unroll
-          for (int l = kAggLevels; l < 16; ++l) {
+          for (int l = kMergeEnd; l < 16; ++l) {
             const float g0 = g[2 * l], g1 = g[2 * l + 1];
             if ((kScatterWarps == 4 || (l < 8) == (lsplit == 0)) && (g0 != 0.f || g1 != 0.f)) {
               const LevelCell c = level_cell(pos, F.scalings[l]);
@@ -387,12 +380,17 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
           }
         }
       }
+      PROF_ADD(t_direct)
     }
+#ifdef FNR_BWD_PROF
+    if (prof) printf("bwd scatter warp: total %lld cycles; waiting for a hand-off %lld, aggregated levels %lld, direct levels %lld\n", clock64() - t_total, t_full, t_agg, t_direct);
+#endif
   } else {
   // ================= compute warps: recompute + dX / dW chain on the tensor cores =================
   reg_inc<kComputeRegs>();
 #pragma unroll 1
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    PROF_MARK()
     const long long p = tile * 128 + row;
     const bool valid = p < N;
     const long long pc = valid ? p : N - 1;
@@ -495,7 +493,9 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
         store_chunk(tDY, 128 * 64 * 2, row, 4 * half + j, dz);
       }
     }
+    PROF_ADD(t_epi)
     named_bar_sync(BAR_EMPTY, kT);  // the scatter warps have copied the previous tile's hand-off out of the C1 region
+    PROF_ADD(t_empty)
     epi32(trow + C_R0 + 32 * half, tC1, row, half, [&](int n, float x) { return fmaxf(x + sf[F_BC0 + n], 0.f); });
     FNR_SYNC_ISSUE(issue_gemm<64, 64>(tb + C_R0, aC1, sb + OFF_WC1); issue_dw<16>(tb + C_AV, aA, aA + LO64, aD16, aD16 + LO16, !first);
                    issue_dw<16>(tb + C_AS0, aDY, aDY + LO64, aGEO, aGEO + LO64, !first))
@@ -613,11 +613,21 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
       if (half == 0) reinterpret_cast<float4*>(stage + row * STAGE_STRIDE + 32)[0] = make_float4(pos.x, pos.y, pos.z, valid ? 1.f : 0.f);
     }
     named_bar_arrive(BAR_FULL, kT);
+    PROF_ADD(t_epi)
+#ifdef FNR_BWD_PROF
+    ++n_tiles;
+#endif
     fence_before_sync();  // this tile's TMEM reads are ordered before the next tile's MMAs (via the next barrier)
     first = false;
   }
 #undef FNR_SYNC_ISSUE
 #undef FNR_WAIT
+#ifdef FNR_BWD_PROF
+  if (prof)
+    printf("bwd compute warp %d: %d tiles, total %lld cycles; epilogues + loads %lld, compute barrier %lld, waiting for the scatter warps %lld, "
+           "MMA waits T1..T9 %lld %lld %lld %lld %lld %lld %lld %lld %lld\n", warp, n_tiles, clock64() - t_total, t_epi, t_bar, t_empty, t_wait[0], t_wait[1],
+           t_wait[2], t_wait[3], t_wait[4], t_wait[5], t_wait[6], t_wait[7], t_wait[8]);
+#endif
   }  // compute warps
 
   // ---- flush the resident accumulators ---------------------------------------------------------------

@@ -131,6 +131,54 @@ __device__ __forceinline__ void scatter_level_aggregated(float2* gtab, const Vec
     }
   }
 }
+// One shuffle round instead of the full scan: the lane at an even position of a same-cell run absorbs its successor and the odd
+// lanes stay silent -- half the red lanes of a long run for 16 shuffles (the full scan: 80).
+__device__ __forceinline__ void scatter_level_merged1(float2* gtab, const Vec3& pos, bool live, float g0, float g1, int l, float scale, int log2T,
+                                                      uint32_t hmask, int lane) {
+  const LevelCell c = level_cell(pos, scale);
+  const uint32_t key = live ? (c.hx[0] ^ c.hy[0] ^ c.hz[0]) : (0x80000000u | (uint32_t)lane);
+  const uint32_t prev = __shfl_up_sync(kTcFullMask, key, 1);
+  const uint32_t heads = __ballot_sync(kTcFullMask, lane == 0 || prev != key);
+  const int run_start = 31 - __clz(heads & ((2u << lane) - 1u));
+  const bool odd = ((lane - run_start) & 1) != 0;  // absorbed by its predecessor
+  const uint32_t odds = __ballot_sync(kTcFullMask, odd);
+  const bool absorb = !odd && lane < 31 && ((odds >> (lane + 1)) & 1u);
+  if (!live) g0 = g1 = 0.f;
+  float v0[8], v1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float w = corner_weight(c, k);
+    v0[k] = w * g0;
+    v1[k] = w * g1;
+  }
+  if (odds != 0u) {  // warp-uniform
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float t0 = __shfl_down_sync(kTcFullMask, v0[k], 1), t1 = __shfl_down_sync(kTcFullMask, v1[k], 1);
+      if (absorb) {
+        v0[k] += t0;
+        v1[k] += t1;
+      }
+    }
+  }
+  if (live && !odd) {
+    const uint32_t base = (uint32_t)l << log2T;
+    const bool pair = ((c.hx[0] & 1u) == 0u) && (c.hx[1] == c.hx[0] + 1u);
+    constexpr int kf[4] = {6, 7, 2, 3}, kc[4] = {5, 4, 1, 0};  // corner pairs (x floor, x ceil) per (y, z)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t rf = corner_row(c, kf[q], hmask, base);
+      if (pair) {
+        const bool f_first = (rf & 1u) == 0u;
+        const float4 v = f_first ? make_float4(v0[kf[q]], v1[kf[q]], v0[kc[q]], v1[kc[q]]) : make_float4(v0[kc[q]], v1[kc[q]], v0[kf[q]], v1[kf[q]]);
+        if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) atomicAdd(reinterpret_cast<float4*>(gtab + (rf & ~1u)), v);
+      } else {
+        if (v0[kf[q]] != 0.f || v1[kf[q]] != 0.f) atomicAdd(gtab + rf, make_float2(v0[kf[q]], v1[kf[q]]));
+        if (v0[kc[q]] != 0.f || v1[kc[q]] != 0.f) atomicAdd(gtab + corner_row(c, kc[q], hmask, base), make_float2(v0[kc[q]], v1[kc[q]]));
+      }
+    }
+  }
+}
 // fine levels: x-neighbours (floor x even, ceil = floor + 1) are adjacent table rows: one 16-byte red instead of two 8-byte ones
 __device__ __forceinline__ void scatter_level_direct(float2* gtab, const Vec3& pos, float g0, float g1, int l, float scale, int log2T, uint32_t hmask) {
   if (g0 == 0.f && g1 == 0.f) return;

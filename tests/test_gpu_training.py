@@ -202,3 +202,92 @@ def test_export_cli_on_a_trained_run(native_lib, cuda_device, tmp_path):
     pcds2 = entrypoint(["semantic-pointcloud", "--load-config", str(run / "config.yml"), "--output-dir", str(out / "grid"), "--num-points-per-side", "40",
                         "--stratified-jitter", "false", "--bounding-box-min", "-0.35", "-0.35", "-0.35", "--bounding-box-max", "0.35", "0.35", "0.35"])
     assert pcds2["density"]["points"].shape[1] == 3
+
+
+def test_trained_model_export_128_matches_oracle(trained, cuda_device):
+    """Uniform 128^3 volume sample of the TRAINED field (deterministic grid) against the oracle: dense density / logit / rgb at
+    1e-3, and the three selected point sets of sample_volume (export/exporter_utils.py:111-153) -- with the reference constants
+    3 / 70 / 0.9 and with data-driven thresholds -- identical away from the thresholds."""
+    from fruitnerf_b200 import ops
+    from oracle import ns_torch as ns
+
+    trainer, _ = trained
+    model = trainer.pipeline.model
+    cfg = model.config
+    n = 128
+    field = model.field
+    saved = field.spatial_distortion
+    field.spatial_distortion = None  # setup_inference (fruit_nerf.py:183)
+    try:
+        fsd = {k: v.detach().cpu() for k, v in field.state_dict().items()}
+        spec = fr.FieldSpec(max_res=cfg.max_res, log2_hashmap_size=cfg.log2_hashmap_size, geo_feat_dim=cfg.geo_feat_dim)
+        aabb = ((-0.35, -0.35, -0.35), (0.35, 0.35, 0.35))
+        pts, plane = ns.surface_points(aabb, n)
+        o, dirs, nears, fars = ns.orthographic_rays(pts, plane, batch=n * n, count=1)
+        with torch.no_grad():
+            ref = fr.export_outputs(fsd, spec, o, dirs, nears, fars, n, chunk=1 << 17)
+        dens, sem = ref["density"].reshape(-1), ref["semantics"].reshape(-1)
+        bins = torch.linspace(0.0, 1.0, n + 1).cuda()
+        for thr in ((3.0, 70.0, 0.9), (float(sem.quantile(0.98)), float(dens.quantile(0.95)), 0.5)):
+            buf = ops.ExportBuffers(capacity=n ** 3, device=cuda_device)
+            dense = None
+            B = 4096
+            outs = []
+            for start in range(0, o.shape[0], B):
+                with torch.no_grad():
+                    outs.append(ops.export_batch(field.kernel_shape(), field.kernel_params(), o[start:start + B].cuda(), [float(v) for v in dirs[0]], bins,
+                                                 float(nears[0]), float(fars[0]), buf, point_base=start * n, dense_out=True, thresholds=thr))
+            dense = {k: torch.cat([d_[k] for d_ in outs]) for k in ("density", "semantics", "rgb", "point_location")}
+            assert torch.equal(dense["point_location"].cpu(), ref["point_location"])
+            assert_rel(dense["density"], ref["density"], what="trained field: density on the 128^3 grid")
+            assert_rel(dense["semantics"], ref["semantics"], floor=0.02, what="trained field: logit on the 128^3 grid")
+            assert_rel(dense["rgb"], ref["rgb"], what="trained field: rgb on the 128^3 grid")
+            lab = torch.heaviside(torch.sigmoid(sem) - thr[2], torch.tensor(0.0))
+            masks = {0: (lab >= 0.999) & (dens >= thr[1]), 1: (sem >= thr[0]) & (dens >= thr[1]), 2: dens >= thr[1]}
+            near_thr = ((sem - thr[0]).abs() < 1e-3 * (1 + abs(thr[0]))) | ((dens - thr[1]).abs() < 1e-3 * (1 + abs(thr[1]))) | (
+                (torch.sigmoid(sem) - thr[2]).abs() < 1e-4)
+            counts = buf.counts.cpu()
+            for k in range(3):
+                got = torch.zeros(n ** 3, dtype=torch.bool)
+                got[buf.keys[k][: int(counts[k])].cpu()] = True
+                diff = got ^ masks[k]
+                assert bool((diff & ~near_thr).sum() == 0), f"set {k}: selection differs away from the thresholds"
+                assert abs(int(counts[k]) - int(masks[k].sum())) <= int(near_thr.sum())
+    finally:
+        field.spatial_distortion = saved
+
+
+def test_model_export_follows_the_sampler_training_flag(trained, cuda_device):
+    """FruitModel.get_export_outputs: jittered per-ray bins while the export sampler module is in training mode (the state the
+    reference exporter runs it in), the regular grid after ``.eval()``."""
+    from fruitnerf_b200.compat import RayBundle
+
+    trainer, _ = trained
+    pipeline = trainer.pipeline
+    model, dm = pipeline.model, pipeline.datamanager
+    saved = (model.proposal_sampler, model.field.spatial_distortion, model.test_mode, dm.config.eval_num_rays_per_batch, dm.train_count)
+    try:
+        pipeline.eval()
+        model.test_mode = "export"
+        model.setup_inference(render_rgb=True, num_inference_samples=16)
+        assert model.proposal_sampler.training  # a module created after pipeline.eval() (scripts/exporter.py:87-95 upstream)
+        dm.config.eval_num_rays_per_batch = 256
+        dm.train_count = 0
+        dm.setup_inference(aabb=((-0.3, -0.3, -0.3), (0.3, 0.3, 0.3)), num_points=16)
+        bundle, _ = dm.next_sample_volume(0)
+        with torch.no_grad():
+            a = model(bundle)
+            b = model(bundle)
+            model.proposal_sampler.eval()
+            c = model(bundle)
+            d = model(bundle)
+        assert not torch.equal(a["point_location"], b["point_location"])  # fresh jitter per call
+        assert torch.equal(c["point_location"], d["point_location"])      # deterministic grid
+        dd = c["point_location"][:, 1:] - c["point_location"][:, :-1]
+        assert torch.allclose(dd, dd[:, :1].expand_as(dd), atol=1e-6)     # equally spaced along the ray
+        # a jittered sample stays within one bin width of the regular grid's sample
+        far = float(bundle.fars[0])
+        assert float((a["point_location"] - c["point_location"]).norm(dim=-1).max()) <= far / 16 * 1.01
+    finally:
+        model.proposal_sampler, model.field.spatial_distortion, model.test_mode, dm.config.eval_num_rays_per_batch, dm.train_count = saved
+        pipeline.train()
