@@ -181,6 +181,15 @@ constexpr int BAR_COMPUTE = 1, BAR_FULL = 2, BAR_EMPTY = 3;
 // warps below); measured on the bench batch (tools/r2/run16.sh, run17.sh): no merge on the coarse levels 0.91 ms, the round-1 full
 // segmented scan (5 shuffle rounds) on levels 0-3 0.843 ms, one round on levels 0-5 / 0-7 / 0-15 0.814 ms.
 constexpr int kMergeEnd = FNR_MERGE_END;
+#ifndef FNR_BWD_OFFLOAD
+#define FNR_BWD_OFFLOAD 6
+#endif
+// The finest kOffload levels of a tile's table gradient are scattered by the chain warps 4-7 themselves (they hold those columns of
+// the encoding gradient in registers at T9), one level inside each of the long MMA waits of the NEXT tile (T4, T6, T7, T9; + T5, T8; + T2, T3):
+// those warps idle there, while the four scatter warps are the critical path of the kernel.
+constexpr int kOffload = FNR_BWD_OFFLOAD;
+static_assert(kOffload == 0 || kOffload == 4 || kOffload == 6 || kOffload == 8, "offloaded levels");
+static_assert(kOffload == 0 || kScatterWarps == 4, "level offload assumes one scatter thread per point");
 
 struct BwdArgs {
   KField F;
@@ -341,10 +350,9 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
       const int lsplit = kScatterWarps == 8 ? ((tid - kTC) >> 7) : 0;
       // Levels 0 .. kMergeEnd-1: the 32 lanes of a warp are consecutive samples of a ray and share grid cells (run length ~25 at
       // level 0, ~2.6 at level 7 on the bench workload).  ONE shuffle round: the lane at an even position of a run of same-cell
-      // lanes absorbs its successor (16 shuffles), which halves the red lanes of these levels.  The full segmented scan of
-      // round 1 (5 rounds, 80 shuffles per level, one issuing lane per run) was slower: every shuffle and every red of these
-      // warps goes through the SM's one memory-instruction queue, so it is instructions, not lanes, that have to be saved
-      // (profiles/r2_red_probe.log, profiles/r2_backward_experiments.md).
+      // lanes absorbs its successor (16 shuffles), which halves the red lanes of these levels.  Measured against the full
+      // segmented scan of round 1 (5 rounds, one issuing lane per run), two rounds, and no merging in
+      // profiles/r2_backward_experiments.md: this is the fastest schedule here.
       if (do_scatter && lsplit == 0) {
 #pragma unroll 1
         for (int l = 0; l < kMergeEnd; ++l) scatter_level_merged1(gtab, pos, live, g[2 * l], g[2 * l + 1], l, F.scalings[l], F.log2T, hmask, lane);
@@ -353,7 +361,7 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
       if (do_scatter) {
         if (live) {
 #pragma unroll
-          for (int l = kMergeEnd; l < 16; ++l) {
+          for (int l = kMergeEnd; l < 16 - kOffload; ++l) {
             const float g0 = g[2 * l], g1 = g[2 * l + 1];
             if ((kScatterWarps == 4 || (l < 8) == (lsplit == 0)) && (g0 != 0.f || g1 != 0.f)) {
               const LevelCell c = level_cell(pos, F.scalings[l]);
@@ -388,6 +396,14 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
   } else {
   // ================= compute warps: recompute + dX / dW chain on the tensor cores =================
   reg_inc<kComputeRegs>();
+  // previous tile's finest levels, scattered by warps 4-7 inside this tile's MMA waits (kOffload > 0)
+  float hold[kOffload > 0 ? 2 * kOffload : 1];
+  Vec3 hold_pos = {0.f, 0.f, 0.f};
+  bool hold_live = false;
+  float2* const gtab_c = reinterpret_cast<float2*>(G.hash_table);
+#define FNR_OFFLOAD_LEVEL(i)                                                                                                        \
+  if (kOffload > (i) && half == 1 && hold_live && !(a.debug_flags & 1))                                                             \
+    scatter_level_direct(gtab_c, hold_pos, hold[2 * (i)], hold[2 * (i) + 1], 16 - kOffload + (i), F.scalings[16 - kOffload + (i)], F.log2T, hmask);
 #pragma unroll 1
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     PROF_MARK()
@@ -444,6 +460,7 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
     epi32(trow + C_R0 + 32 * half, tH, row, half, [&](int n, float x) { return fmaxf(x + sf[F_B0 + n], 0.f); });
     FNR_SYNC_ISSUE(issue_gemm<64, 16>(tb + C_R1, aH, sb + OFF_W1))
 
+    FNR_OFFLOAD_LEVEL(6)
     // ---- T2: [h0 | geo] ; geo chunks ; dlogit tile ; semantic0 + colour0 --------------------------------
     FNR_WAIT()
     float d_h0;
@@ -473,6 +490,7 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
     }
     FNR_SYNC_ISSUE(issue_gemm_lo<16, 64>(tb + C_R2, aGEO, aGEO + LO64, sb + OFF_WS0); issue_gemm<64, 64>(tb + C_R0, aCIN, sb + OFF_WC0))
 
+    FNR_OFFLOAD_LEVEL(7)
     // ---- T3: z1 -> A, dz1 -> DY, c1 -> C1 ; colour1 + AV + AS0 ----------------------------------------
     FNR_WAIT()
     {
@@ -500,6 +518,7 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
     FNR_SYNC_ISSUE(issue_gemm<64, 64>(tb + C_R0, aC1, sb + OFF_WC1); issue_dw<16>(tb + C_AV, aA, aA + LO64, aD16, aD16 + LO16, !first);
                    issue_dw<16>(tb + C_AS0, aDY, aDY + LO64, aGEO, aGEO + LO64, !first))
 
+    FNR_OFFLOAD_LEVEL(0)
     // ---- T4: c2 -> A ; do3 -> D16 ; AC2 + dc2 -----------------------------------------------------------
     FNR_WAIT()
     epi32(trow + C_R0 + 32 * half, tA, row, half, [&](int n, float x) { return fmaxf(x + sf[F_BC1 + n], 0.f); });
@@ -521,17 +540,20 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
     }
     FNR_SYNC_ISSUE(issue_dw<16>(tb + C_AC2, aA, aA + LO64, aD16, aD16 + LO16, !first); issue_dx<16, 64>(tb + C_R2, aD16, sb + OFF_WC2))
 
+    FNR_OFFLOAD_LEVEL(4)
     // ---- T5: dc2 = (do3 Wc2) * relu'(c2) -> DY ; AC1, AC1b, dc1 ----------------------------------------
     FNR_WAIT()
     epi32_masked(trow + C_R2 + 32 * half, tA, tDY, row, half);
     FNR_SYNC_ISSUE(issue_dw<64>(tb + C_AC1, aDY, aDY + LO64, aC1, aC1 + LO64, !first); issue_dw<16>(tb + C_AC1B, aDY, aDY + LO64, aONES, 0u, !first);
                    issue_dx<64, 64>(tb + C_R0, aDY, sb + OFF_WC1))
 
+    FNR_OFFLOAD_LEVEL(1)
     // ---- T6: dc1 = (dc2 Wc1) * relu'(c1) -> DY ; AC0, dcin --------------------------------------------
     FNR_WAIT()
     epi32_masked(trow + C_R0 + 32 * half, tC1, tDY, row, half);
     FNR_SYNC_ISSUE(issue_dw<64>(tb + C_AC0, aDY, aDY + LO64, aCIN, aCIN + LO64, !first); issue_dx<64, 64>(tb + C_R2, aDY, sb + OFF_WC0))
 
+    FNR_OFFLOAD_LEVEL(2)
     // ---- T7: dcin -> d_app (embedding gradient), d_geo ; dout16 -> D16 ; AB1, dh1 -----------------------
     FNR_WAIT()
     {
@@ -587,6 +609,7 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
     }
     FNR_SYNC_ISSUE(issue_dw<16>(tb + C_AB1, aH, aH + LO64, aD16, aD16 + LO16, !first); issue_dx<16, 64>(tb + C_R0, aD16, sb + OFF_W1))
 
+    FNR_OFFLOAD_LEVEL(5)
     // ---- T8: dh1 = (dout W1) * relu'(h1) -> DY ; reload enc -> A ; AB0, AB0b, denc ------------------------
     FNR_WAIT()
     epi32_masked(trow + C_R0 + 32 * half, tH, tDY, row, half);
@@ -600,6 +623,7 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
     FNR_SYNC_ISSUE(issue_dw<32>(tb + C_AB0, aDY, aDY + LO64, aA, aA + LO32, !first); issue_dw<16>(tb + C_AB0B, aDY, aDY + LO64, aONES, 0u, !first);
                    issue_dx<64, 32>(tb + C_R2, aDY, sb + OFF_W0))
 
+    FNR_OFFLOAD_LEVEL(3)
     // ---- T9: denc -> hand-off to the scatter warps (C1 region is idle since T6) ------------------------------
     FNR_WAIT()
     {
@@ -611,6 +635,12 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
       for (int q = 0; q < 4; ++q)
         dst[q] = make_float4(__uint_as_float(r0[4 * q]), __uint_as_float(r0[4 * q + 1]), __uint_as_float(r0[4 * q + 2]), __uint_as_float(r0[4 * q + 3]));
       if (half == 0) reinterpret_cast<float4*>(stage + row * STAGE_STRIDE + 32)[0] = make_float4(pos.x, pos.y, pos.z, valid ? 1.f : 0.f);
+      if (kOffload > 0 && half == 1) {  // columns 32 - 2 kOffload .. 31 = levels 16 - kOffload .. 15
+#pragma unroll
+        for (int i = 0; i < 2 * kOffload; ++i) hold[i] = __uint_as_float(r0[16 - 2 * kOffload + i]);
+        hold_pos = pos;
+        hold_live = valid;
+      }
     }
     named_bar_arrive(BAR_FULL, kT);
     PROF_ADD(t_epi)
@@ -620,6 +650,8 @@ __global__ void __launch_bounds__(kT, 1) tc_field_backward_kernel(const __grid_c
     fence_before_sync();  // this tile's TMEM reads are ordered before the next tile's MMAs (via the next barrier)
     first = false;
   }
+  FNR_OFFLOAD_LEVEL(0) FNR_OFFLOAD_LEVEL(1) FNR_OFFLOAD_LEVEL(2) FNR_OFFLOAD_LEVEL(3) FNR_OFFLOAD_LEVEL(4) FNR_OFFLOAD_LEVEL(5) FNR_OFFLOAD_LEVEL(6) FNR_OFFLOAD_LEVEL(7)  // the last tile's
+#undef FNR_OFFLOAD_LEVEL
 #undef FNR_SYNC_ISSUE
 #undef FNR_WAIT
 #ifdef FNR_BWD_PROF

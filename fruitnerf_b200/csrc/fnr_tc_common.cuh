@@ -74,6 +74,27 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 }
 
 
+// The 8 corner contributions (v0[k], v1[k]) of one point at one level.  x-neighbour corners are adjacent table rows r, r^1 when the
+// floor x is even: one 16-byte red for both (the cost of a red is per lane, not per byte: profiles/r2_red_probe.log); otherwise two
+// 8-byte reds.  (Issuing 16-byte reds with a zero half for the unpaired lanes as well -- 8 instead of 12 red instructions per warp and
+// level -- measured the same time.)
+__device__ __forceinline__ void corner_reds(float2* gtab, const LevelCell& c, const float (&v0)[8], const float (&v1)[8], uint32_t hmask, uint32_t base) {
+  const bool pair = ((c.hx[0] & 1u) == 0u) && (c.hx[1] == c.hx[0] + 1u);
+  constexpr int kf[4] = {6, 7, 2, 3}, kc[4] = {5, 4, 1, 0};  // corner pairs (x floor, x ceil) per (y, z)
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t rf = corner_row(c, kf[q], hmask, base);
+    if (pair) {
+      const bool f_first = (rf & 1u) == 0u;
+      const float4 v = f_first ? make_float4(v0[kf[q]], v1[kf[q]], v0[kc[q]], v1[kc[q]]) : make_float4(v0[kc[q]], v1[kc[q]], v0[kf[q]], v1[kf[q]]);
+      if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) atomicAdd(reinterpret_cast<float4*>(gtab + (rf & ~1u)), v);
+    } else {
+      if (v0[kf[q]] != 0.f || v1[kf[q]] != 0.f) atomicAdd(gtab + rf, make_float2(v0[kf[q]], v1[kf[q]]));
+      if (v0[kc[q]] != 0.f || v1[kc[q]] != 0.f) atomicAdd(gtab + corner_row(c, kc[q], hmask, base), make_float2(v0[kc[q]], v1[kc[q]]));
+    }
+  }
+}
+
 // ---- hash-table gradient of one level for a warp of points (lane = point; the 32 lanes are consecutive samples of a ray) ----------
 // Coarse / middle levels: consecutive lanes share grid cells.  A run of lanes in the same cell is summed with a segmented suffix scan
 // and only its head lane issues the reds (run length ~25 at level 0, ~9 at level 3, ~2 at level 8 on the bench batch); x-neighbour
@@ -132,7 +153,8 @@ __device__ __forceinline__ void scatter_level_aggregated(float2* gtab, const Vec
   }
 }
 // One shuffle round instead of the full scan: the lane at an even position of a same-cell run absorbs its successor and the odd
-// lanes stay silent -- half the red lanes of a long run for 16 shuffles (the full scan: 80).
+// lanes stay silent -- half the red lanes of a long run for 16 shuffles (the full scan: 80).  (Two rounds -- blocks of four lanes --
+// measured slower in the small backward: 0.806 against 0.791 ms, profiles/r2_backward_experiments.md.)
 __device__ __forceinline__ void scatter_level_merged1(float2* gtab, const Vec3& pos, bool live, float g0, float g1, int l, float scale, int log2T,
                                                       uint32_t hmask, int lane) {
   const LevelCell c = level_cell(pos, scale);
@@ -161,23 +183,7 @@ __device__ __forceinline__ void scatter_level_merged1(float2* gtab, const Vec3& 
       }
     }
   }
-  if (live && !odd) {
-    const uint32_t base = (uint32_t)l << log2T;
-    const bool pair = ((c.hx[0] & 1u) == 0u) && (c.hx[1] == c.hx[0] + 1u);
-    constexpr int kf[4] = {6, 7, 2, 3}, kc[4] = {5, 4, 1, 0};  // corner pairs (x floor, x ceil) per (y, z)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t rf = corner_row(c, kf[q], hmask, base);
-      if (pair) {
-        const bool f_first = (rf & 1u) == 0u;
-        const float4 v = f_first ? make_float4(v0[kf[q]], v1[kf[q]], v0[kc[q]], v1[kc[q]]) : make_float4(v0[kc[q]], v1[kc[q]], v0[kf[q]], v1[kf[q]]);
-        if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) atomicAdd(reinterpret_cast<float4*>(gtab + (rf & ~1u)), v);
-      } else {
-        if (v0[kf[q]] != 0.f || v1[kf[q]] != 0.f) atomicAdd(gtab + rf, make_float2(v0[kf[q]], v1[kf[q]]));
-        if (v0[kc[q]] != 0.f || v1[kc[q]] != 0.f) atomicAdd(gtab + corner_row(c, kc[q], hmask, base), make_float2(v0[kc[q]], v1[kc[q]]));
-      }
-    }
-  }
+  if (live && !odd) corner_reds(gtab, c, v0, v1, hmask, (uint32_t)l << log2T);
 }
 // fine levels: x-neighbours (floor x even, ceil = floor + 1) are adjacent table rows: one 16-byte red instead of two 8-byte ones
 __device__ __forceinline__ void scatter_level_direct(float2* gtab, const Vec3& pos, float g0, float g1, int l, float scale, int log2T, uint32_t hmask) {

@@ -1,0 +1,20 @@
+#!/bin/bash
+# small backward: 16-byte-only reds, 8 scatter warps
+mkdir -p gpurun_out
+T="timeout -s KILL"
+for v in default V1 V2 S8 V3 V4 default V1; do
+  if [ "$v" = default ]; then unset FNR_LIB; else export FNR_LIB=$PWD/tools/bin/libfnr_$v.so; fi
+  $T 100 python bench.py --steps 30 --warmup 3 --no-cpu --no-train --no-variants > gpurun_out/r2_bench_$v.json 2> gpurun_out/r2_bench_$v.err; rc=$?
+  python - <<PY
+import json
+try:
+    j=json.loads(open('gpurun_out/r2_bench_$v.json').read())
+    print('small $v rc=$rc', {k:round(j[k],4) for k in ('value','ms_per_step','fwd_ms','bwd_ms')}, 'e2e', int(j['e2e']['value']))
+except Exception as e:
+    print('$v rc=$rc parse failed', e); print(open('gpurun_out/r2_bench_$v.err').read()[-600:])
+PY
+done
+for v in V1 V2; do
+FNR_LIB=$PWD/tools/bin/libfnr_$v.so $T 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py tests/test_gpu_golden.py -m gpu -x -q --timeout 120 -k "(backward or gradients) and not big" > gpurun_out/r2_pytest_$v.log 2>&1; echo "$v parity rc=$?"; tail -2 gpurun_out/r2_pytest_$v.log | cut -c1-300
+done
+FNR_LIB=$PWD/tools/bin/libfnr_V1prof.so $T 120 python tools/profile_driver.py small 3 > gpurun_out/r2_bwd_prof_V1.log 2>&1; echo "prof rc=$?"; grep "^bwd" gpurun_out/r2_bwd_prof_V1.log | tail -3
