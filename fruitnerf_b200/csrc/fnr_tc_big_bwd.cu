@@ -31,6 +31,8 @@ constexpr int kScatterThreads = 128;  // 4 warps: hash-table gradient reds of th
                                       // (8 scatter warps measured slower: 3.32 vs 3.07 ms backward phase -- the reds contend)
 constexpr int kCtaThreads = kComputeThreads + kScatterThreads;
 constexpr int BAR_COMPUTE = 1, BAR_FULL = 2, BAR_EMPTY = 3;
+constexpr int kChainLevelsDefault = 8;  // level-major mode: coarsest levels still scattered by the chain kernel's scatter warps (at most 8; measured
+                                        // backward phase: 0 levels 2.125 ms, 4: 2.080, 6: 2.054, 8: 1.998; 10 / 12 / 16 levels: 2.15 / 2.17 / 2.32)
 constexpr int kAggLevels = 4;    // coarse levels whose reds are run-length aggregated across the warp
 constexpr int STAGE_STRIDE = 36;  // floats per point in the hand-off buffer: denc[32], pos xyz, live flag
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -97,6 +99,9 @@ struct ChainArgs {
   const float* stash;
   const float* sample_rgb;
   float* denc;       // [N,32] encoding gradient for the level-major scatter of tc_big_dw_kernel, or NULL: scatter warps of this kernel
+  int chain_levels;  // with denc: the coarsest chain_levels levels are still scattered here, tile by tile, by the (otherwise idle) scatter
+                     // warps -- their slices of the gradient table are small enough to stay L2-resident -- and tc_big_dw_kernel starts above
+  int chain_merge;   // 0: full segmented scan on those levels, 1: one merge round
   uint8_t* records;  // scratch: ceil(N / 64) records of kRecBytes
   float* fold;       // [kFoldFloats] zero-initialised: the chain adds s = sum dlogit at [128]
   int debug_flags;   // FNR_DEBUG_BWD (timing experiments only): bit 0 skip the table scatter, bit 2 skip the X / dY stores
@@ -254,7 +259,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
     // ================= scatter warps: hash-table gradient reds, decoupled from the tensor chain =================
     reg_dec<72>();
     const bool do_scatter = !(a.debug_flags & 1);
-    if (!a.denc) {  // (with a.denc the encoding gradient goes to global memory and tc_big_dw_kernel scatters it level by level)
+    if (!a.denc || a.chain_levels > 0) {  // (with a.denc the encoding gradient goes to global memory and tc_big_dw_kernel scatters the levels
+                                          // from chain_levels on, level by level)
     named_bar_arrive(BAR_EMPTY, kCtaThreads);
 #pragma unroll 1
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -270,7 +276,20 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
       if (tile + gridDim.x < tiles) named_bar_arrive(BAR_EMPTY, kCtaThreads);  // the hand-off buffer may be overwritten
       const Vec3 pos = {pv.x, pv.y, pv.z};
       const bool live = pv.w != 0.f;
-      if (do_scatter) {
+      if (do_scatter && a.denc) {
+#pragma unroll 1
+        for (int l = 0; l < a.chain_levels; ++l) {
+          float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+          for (int ll = 0; ll < 8; ++ll)
+            if (ll == l) {
+              g0 = g[2 * ll];
+              g1 = g[2 * ll + 1];
+            }
+          if (a.chain_merge) scatter_level_merged1(gtab, pos, live, g0, g1, l, F.scalings[l], F.log2T, hmask, lane);
+          else scatter_level_aggregated(gtab, pos, live, g0, g1, l, F.scalings[l], F.log2T, hmask, lane);
+        }
+      } else if (do_scatter) {
 #pragma unroll 1
         for (int l = 0; l < kAggLevels; ++l) {
           float g0 = 0.f, g1 = 0.f;
@@ -617,7 +636,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
           store8(dst + 8, __uint_as_float(r[8]), __uint_as_float(r[9]), __uint_as_float(r[10]), __uint_as_float(r[11]), __uint_as_float(r[12]),
                  __uint_as_float(r[13]), __uint_as_float(r[14]), __uint_as_float(r[15]));
         }
-      } else {
+      }
+      if (!a.denc || a.chain_levels > 0) {
         named_bar_sync(BAR_EMPTY, kCtaThreads);  // the scatter warps have copied the previous tile out
         float4* dst = reinterpret_cast<float4*>(stage + row * STAGE_STRIDE + 16 * half);
 #pragma unroll
@@ -626,7 +646,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc_big_backward_chain_kernel(c
         if (half == 0) reinterpret_cast<float4*>(stage + row * STAGE_STRIDE + 32)[0] = make_float4(pos.x, pos.y, pos.z, in_range ? 1.f : 0.f);
       }
     }
-    if (!a.denc) named_bar_arrive(BAR_FULL, kCtaThreads);
+    if (!a.denc || a.chain_levels > 0) named_bar_arrive(BAR_FULL, kCtaThreads);
     fence_before_sync();
   }
   // flush the running sums: warp reduce, one atomic per warp and value
@@ -688,6 +708,7 @@ struct DwArgs {
   float* fold;  // [kFoldFloats]: v[128] (+= over CTAs); [128] = s comes from the chain kernel
   // level-major hash-table gradient scatter by the six otherwise idle warps (denc == NULL: the chain kernel scattered already)
   const float* denc;  // [N,32]
+  int first_level;    // levels below were scattered by the chain kernel
   KField F;
   KRays Rr;
   long long num_points;
@@ -818,7 +839,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) tc_big_dw_kernel(const __grid_c
     const long long chunks = (N + 31) / 32;
     const int S = a.Rr.S;
 #pragma unroll 1
-    for (int l = 0; l < F.L; ++l) {
+    for (int l = a.first_level; l < F.L; ++l) {
       const float scale = F.scalings[l];
 #pragma unroll 1
       for (long long c = (long long)blockIdx.x * kSW + sw; c < chunks; c += (long long)gridDim.x * kSW) {
@@ -1007,6 +1028,11 @@ int launch_tc_big_field_backward(const KField& F, const KParams& P, const KParam
   // FNR_BIG_BWD_MODE=0: round-1 placement of the table scatter (scatter warps inside the chain kernel), for A/B timing
   static const bool level_major = !(getenv("FNR_BIG_BWD_MODE") && atoi(getenv("FNR_BIG_BWD_MODE")) == 0);
   a.denc = level_major ? reinterpret_cast<float*>(base + 1024 + (size_t)(2 * tiles) * kRecBytes) : nullptr;
+  // FNR_BIG_CHAIN_LEVELS / FNR_BIG_CHAIN_MERGE: A/B switches of the hybrid placement (defaults = the measured best)
+  static const int chain_levels = getenv("FNR_BIG_CHAIN_LEVELS") ? atoi(getenv("FNR_BIG_CHAIN_LEVELS")) : kChainLevelsDefault;
+  static const int chain_merge = getenv("FNR_BIG_CHAIN_MERGE") ? atoi(getenv("FNR_BIG_CHAIN_MERGE")) : 0;
+  a.chain_levels = level_major ? (chain_levels < 0 ? 0 : chain_levels > 8 ? 8 : chain_levels) : 0;
+  a.chain_merge = chain_merge;
   if (int rc = check_cuda(cudaMemsetAsync(a.fold, 0, kFoldFloats * sizeof(float), st), "cudaMemsetAsync(fold)")) return rc;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   tc_big_backward_chain_kernel<<<grid, kCtaThreads, kSmemBytes, st>>>(a);
@@ -1019,6 +1045,7 @@ int launch_tc_big_field_backward(const KField& F, const KParams& P, const KParam
   d.G = G;
   d.fold = a.fold;
   d.denc = (a.debug_flags & 1) ? nullptr : a.denc;
+  d.first_level = a.chain_levels;
   d.F = F;
   d.Rr = Rr;
   d.num_points = N;

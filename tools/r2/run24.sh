@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out
+T="timeout -s KILL"
+for cfg in "8 0" "10 0" "12 0" "16 0"; do
+  set -- $cfg
+  FNR_BIG_CHAIN_LEVELS=$1 FNR_BIG_CHAIN_MERGE=$2 $T 100 python bench.py --variant big --steps 15 --warmup 3 --no-cpu --no-train --no-variants > gpurun_out/r2_bench_big_h$1_$2.json 2> gpurun_out/r2_bench_big_h$1_$2.err; rc=$?
+  python - <<PY
+import json
+try:
+    j=json.loads(open('gpurun_out/r2_bench_big_h$1_$2.json').read())
+    print('big chain_levels=$1 merge=$2 rc=$rc', {k:round(j[k],4) for k in ('value','ms_per_step','fwd_ms','bwd_ms')})
+except Exception as e:
+    print('$cfg rc=$rc parse failed', e); print(open('gpurun_out/r2_bench_big_h$1_$2.err').read()[-600:])
+PY
+done
