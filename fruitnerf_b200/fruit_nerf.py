@@ -294,6 +294,14 @@ class FruitModel(nn.Module):
         metrics["distortion"] = ops.distortion_metric(outputs["weights_list"][-1][..., 0], _sdist(outputs["ray_samples_list"][-1]))
         return metrics
 
+    def get_image_metrics_and_images(self, outputs: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor]):
+        """fruit_nerf.py:403-458: metrics (psnr, ssim, iou; lpips needs downloaded weights and is omitted; ``fruit_iou`` added) and
+        the images a logger / viewer shows, for ONE full image rendered by get_outputs_for_camera_ray_bundle.  Computed on the
+        device the rendered outputs live on (the chunked renderer returns CPU tensors, as upstream)."""
+        from .image_metrics import image_metrics_and_images
+
+        return image_metrics_and_images(outputs, batch, self.config.num_proposal_iterations, outputs["rgb"].device)
+
     def _fused_losses(self, outputs, batch):
         """(MSELoss, semantic_loss_weight * BCEWithLogitsLoss, PSNR) from ONE launch, shared by get_metrics_dict and
         get_loss_dict (the reference evaluates the MSE twice, fruit_nerf.py:361 and :398)."""

@@ -88,28 +88,53 @@ class FruitPipeline(nn.Module):
 
     @torch.no_grad()
     def get_eval_image_metrics_and_images(self, step: int):
-        """fruit_pipeline.py:165-190: render one held-out image, PSNR against the ground truth (the reference's SSIM /
-        LPIPS come from torchmetrics, which is not available offline), plus the fruit-mask agreement of the semantic map."""
+        """fruit_pipeline.py:155-172: render one held-out image and hand it to the model's get_image_metrics_and_images
+        (psnr / ssim / iou as upstream, plus ``fruit_iou``: the fruit-mask agreement of the thresholded semantic map)."""
         was_training = self.training
         self.eval()
         image_idx, camera_ray_bundle, batch = self.datamanager.next_eval_image(step)
         outputs = self.model.get_outputs_for_camera_ray_bundle(camera_ray_bundle)
-        image = batch["image"].cpu()
-        mse = torch.mean((outputs["rgb"] - image) ** 2)
-        pred_fruit = (torch.sigmoid(outputs["semantics"]) > 0.9).float()
-        gt = batch["fruit_mask"].cpu()
-        inter, union = float((pred_fruit * gt).sum()), float(((pred_fruit + gt) > 0).float().sum())
-        metrics = {"psnr": float(-10.0 * torch.log10(mse)), "fruit_iou": inter / union if union > 0 else 1.0, "image_idx": image_idx,
-                   "num_rays": int(image.shape[0] * image.shape[1])}
+        metrics, images = self.model.get_image_metrics_and_images(outputs, batch)
+        assert "image_idx" not in metrics
+        metrics["image_idx"] = image_idx
+        assert "num_rays" not in metrics
+        metrics["num_rays"] = int(camera_ray_bundle.origins.shape[0] * camera_ray_bundle.origins.shape[1])
         self.train(was_training)
-        return metrics, {"img": torch.cat([image, outputs["rgb"]], dim=1), "semantics": outputs["semantics"], "depth": outputs["depth"]}
+        return metrics, images
 
     @torch.no_grad()
-    def get_average_eval_image_metrics(self, step: Optional[int] = None) -> Dict[str, float]:
-        """fruit_pipeline.py:192-227: mean of the per-image metrics over the eval split."""
+    def get_average_eval_image_metrics(self, step: Optional[int] = None, output_path=None) -> Dict[str, float]:
+        """fruit_pipeline.py:174-227: mean of every per-image metric over the eval split (plus rays/s of the renders);
+        ``output_path``: also write each image of the images dict as ``<camera>-<key>.jpg``."""
+        import time
+
         n = len(self.datamanager.eval_dataset)
-        rows = [self.get_eval_image_metrics_and_images(step or 0)[0] for _ in range(n)]
-        return {k: float(sum(r[k] for r in rows) / n) for k in ("psnr", "fruit_iou")}
+        rows = []
+        for _ in range(n):
+            t0 = time.time()
+            metrics, images = self.get_eval_image_metrics_and_images(step or 0)
+            metrics["num_rays_per_sec"] = metrics["num_rays"] / max(time.time() - t0, 1e-9)
+            metrics["fps"] = metrics["num_rays_per_sec"] / metrics["num_rays"]
+            if output_path is not None:
+                self._save_eval_images(output_path, metrics["image_idx"], images)
+            rows.append(metrics)
+        return {k: float(sum(r[k] for r in rows) / n) for k in rows[0] if k not in ("image_idx", "num_rays")}
+
+    @staticmethod
+    def _save_eval_images(output_path, image_idx: int, images: Dict[str, torch.Tensor]) -> None:
+        """fruit_pipeline.py:205-210: ``<camera>-<key>.jpg`` per entry of the images dict."""
+        import pathlib
+
+        import numpy as np
+        from PIL import Image
+
+        out = pathlib.Path(output_path)
+        out.mkdir(parents=True, exist_ok=True)
+        for key, val in images.items():
+            arr = (val.detach().float().clamp(0, 1) * 255).byte().cpu().numpy()
+            if arr.ndim == 3 and arr.shape[-1] == 1:
+                arr = np.repeat(arr, 3, axis=-1)
+            Image.fromarray(arr).save(out / f"{image_idx:06d}-{key}.jpg")
 
     def sync_gradients(self):
         """Call after ``loss.backward()``: one collective over the flat gradient buffer."""
