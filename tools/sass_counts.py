@@ -63,7 +63,7 @@ def main():
     for name, tot, c, (reg, stack, shared) in rows:
         print(f"| `{name}` | {reg} | {stack} | {shared} | {tot} | " + " | ".join(str(c.get(k, 0)) for k in KEYS) + " |")
     print("\n(regs / stack / static shared memory: `cuobjdump -res-usage`; the tensor-core kernels take their dynamic shared memory at launch and "
-          "re-balance registers per role with `setmaxnreg`; stack bytes on the simt kernels are per-thread activation arrays, on the tensor kernels 0 = no spills.)")
+          "re-balance registers per role with `setmaxnreg`; stack bytes on the simt kernels are per-thread activation arrays, on the tensor kernels at most 128 B (a dynamically indexed register array, not spill traffic in the loops).)")
     total = collections.Counter()
     for c in counts.values():
         total.update(c)
