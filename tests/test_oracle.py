@@ -295,3 +295,146 @@ def test_gradient_golden_is_reproducible():
     assert np.allclose(sdg["mlp_base_grid.hash_table"].grad[torch.from_numpy(g["g_table_rows"])].numpy(), g["g_table_vals"], rtol=1e-4,
                        atol=1e-6 * np.abs(g["g_table_vals"]).max())
     # the semantic branch is detached from the geometry features (fruit_field.py:264-265): the colour loss alone reaches the base MLP
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Independent pins: the oracle's building blocks against third-party implementations of the same mathematics that ARE
+# installed here (scipy, numpy) or against brute-force evaluations of the published definitions.  They do not replace
+# golden vectors from nerfstudio itself (tools/regen_golden_from_nerfstudio.py), but they are not the oracle checking itself.
+# --------------------------------------------------------------------------------------------------------------
+def _real_sh_scipy(l: int, m: int, d: np.ndarray) -> np.ndarray:
+    """Real spherical harmonic Y_lm (the table convention: positive leading coefficients, no Condon-Shortley sign in the real
+    form) built from scipy's complex harmonics."""
+    from scipy.special import sph_harm_y
+
+    polar = np.arccos(np.clip(d[:, 2], -1, 1))
+    azim = np.arctan2(d[:, 1], d[:, 0])
+    if m == 0:
+        return sph_harm_y(l, 0, polar, azim).real
+    y = sph_harm_y(l, abs(m), polar, azim)
+    return math.sqrt(2.0) * (-1) ** m * (y.real if m > 0 else y.imag)
+
+
+def test_sh_degree4_matches_scipy_real_spherical_harmonics():
+    """All 16 components (constants, polynomial forms, ordering l^2 + l + m) on random unit directions."""
+    g = torch.Generator().manual_seed(5)
+    d = torch.nn.functional.normalize(torch.randn(256, 3, generator=g, dtype=torch.float64), dim=-1)
+    got = ns.sh_degree4(d).numpy()
+    for l in range(4):
+        for m in range(-l, l + 1):
+            want = _real_sh_scipy(l, m, d.numpy())
+            assert np.allclose(got[:, l * l + l + m], want, atol=1e-9), (l, m)
+
+
+def test_pdf_sample_matches_numpy_inverse_cdf():
+    """PDFSampler = piecewise-linear inverse CDF of the padded histogram: numpy's interp(u, cdf, bins) ray by ray."""
+    g = torch.Generator().manual_seed(6)
+    R, S, n = 32, 24, 17
+    w = torch.rand(R, S, generator=g) ** 3
+    w[3] = 0.0  # an empty ray: uniform after the histogram padding
+    edges = torch.sort(torch.rand(R, S + 1, generator=g), dim=-1).values
+    for u_rand in (None, torch.rand(R, 1, generator=g), torch.rand(R, n + 1, generator=g)):
+        got = ns.pdf_sample(w, edges, n, u_rand).double().numpy()
+        nb = n + 1
+        for r in range(R):
+            ww = w[r].double().numpy() + 0.01
+            cdf = np.concatenate([[0.0], np.minimum(1.0, np.cumsum(ww / ww.sum()))])
+            u = np.linspace(0.0, 1.0 - 1.0 / nb, nb)
+            u = u + (1.0 / (2 * nb) if u_rand is None else u_rand[r].double().numpy() / nb)
+            want = np.interp(u, cdf, edges[r].double().numpy())
+            assert np.allclose(got[r], want, atol=2e-6), r
+
+
+def test_get_weights_matches_the_product_form():
+    """w_i = alpha_i * prod_{j<i} (1 - alpha_j) (the discrete volume-rendering quadrature) in float64 loops."""
+    g = torch.Generator().manual_seed(7)
+    R, S = 16, 40
+    deltas = torch.rand(R, S, 1, generator=g) * 0.1
+    dens = torch.rand(R, S, 1, generator=g) ** 4 * 200
+    got = ns.get_weights(deltas, dens)[..., 0].double().numpy()
+    a = 1.0 - np.exp(-(dens * deltas)[..., 0].double().numpy())
+    for r in range(R):
+        T = 1.0
+        for i in range(S):
+            assert got[r, i] == pytest.approx(a[r, i] * T, abs=2e-6)
+            T *= 1.0 - a[r, i]
+
+
+def test_interlevel_loss_matches_the_outer_measure_definition():
+    """mip-NeRF 360's proposal loss: for each interval of the fine histogram, the bound is the total proposal weight of every
+    proposal interval that overlaps it; loss = mean(max(0, w - bound)^2 / (w + eps)).  Brute force over interval pairs."""
+    g = torch.Generator().manual_seed(8)
+    R = 6
+    fine_t = torch.sort(torch.rand(R, 13, generator=g), dim=-1).values
+    fine_w = torch.rand(R, 12, generator=g)
+    fine_w = fine_w / fine_w.sum(-1, keepdim=True)
+    total = 0.0
+    props = []
+    for S in (20, 9):
+        t = torch.sort(torch.rand(R, S + 1, generator=g), dim=-1).values
+        t[:, 0], t[:, -1] = 0.0, 1.0
+        w = torch.rand(R, S, generator=g) * 0.1
+        props.append((t, w))
+        acc = 0.0
+        for r in range(R):
+            for i in range(12):
+                lo, hi = float(fine_t[r, i]), float(fine_t[r, i + 1])
+                bound = sum(float(w[r, j]) for j in range(S) if float(t[r, j + 1]) > lo and float(t[r, j]) < hi)
+                wi = float(fine_w[r, i])
+                acc += max(0.0, wi - bound) ** 2 / (wi + 1e-7)
+        total += acc / (R * 12)
+    got = ns.interlevel_loss([w for _, w in props] + [fine_w], [t for t, _ in props] + [fine_t])
+    assert float(got) == pytest.approx(total, rel=1e-4)
+    assert total > 0
+
+
+def test_scene_contraction_and_lindisp_are_inverses_and_bounded():
+    """Published forms: contract(x) = x inside the unit L-inf ball, (2 - 1/|x|) x/|x| outside (mip-NeRF 360, L-inf variant);
+    s(t) = t/2 below 1, 1 - 1/(2t) above, and its inverse."""
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(512, 3, generator=g) * 4
+    c = ns.scene_contraction_inf(x)
+    n = x.abs().amax(-1)
+    inside = n <= 1
+    assert torch.equal(c[inside], x[inside])
+    assert float(c.abs().amax()) < 2.0
+    assert torch.allclose(c[~inside].abs().amax(-1), 2 - 1 / n[~inside], atol=1e-6)
+    assert torch.allclose(torch.nn.functional.normalize(c[~inside], dim=-1), torch.nn.functional.normalize(x[~inside], dim=-1), atol=1e-6)
+    t = torch.rand(256, generator=g) * 20 + 1e-3
+    s = ns.lindisp_piecewise_fn(t)
+    assert float(s.min()) > 0 and float(s.max()) < 1
+    assert torch.allclose(ns.lindisp_piecewise_inv(s), t, rtol=2e-4)
+    assert torch.allclose(s[t < 1], t[t < 1] / 2) and torch.allclose(s[t >= 1], 1 - 1 / (2 * t[t >= 1]))
+
+
+def test_distortion_loss_is_the_integral_it_closes():
+    """mip-NeRF 360's distortion loss is the closed form of  integral integral p(u) p(v) |u - v| du dv  for the piecewise-constant
+    density p = w_i / delta_i: midpoint quadrature of that double integral on a fine grid."""
+    g = torch.Generator().manual_seed(10)
+    S, G = 9, 3000
+    t = torch.sort(torch.rand(1, S + 1, generator=g, dtype=torch.float64), dim=-1).values
+    t[:, 0], t[:, -1] = 0.0, 1.0
+    w = torch.rand(1, S, generator=g, dtype=torch.float64)
+    u = (torch.arange(G, dtype=torch.float64) + 0.5) / G
+    idx = torch.clamp(torch.searchsorted(t[0], u, right=True) - 1, 0, S - 1)
+    p = (w[0] / (t[0, 1:] - t[0, :-1]))[idx]
+    want = float((p[:, None] * p[None, :] * (u[:, None] - u[None, :]).abs()).sum() / (G * G))
+    assert float(ns.distortion_loss(w, t)) == pytest.approx(want, rel=2e-3)
+
+
+def test_median_depth_is_the_first_sample_reaching_half_the_weight():
+    g = torch.Generator().manual_seed(11)
+    R, S = 64, 30
+    w = torch.rand(R, S, 1, generator=g) ** 2
+    w = w / w.sum(1, keepdim=True) * torch.rand(R, 1, 1, generator=g) * 1.2  # some rays never reach 0.5
+    starts = torch.sort(torch.rand(R, S + 1, generator=g), dim=-1).values
+    depth, idx = ns.render_depth_median(w, starts[:, :-1, None], starts[:, 1:, None])
+    for r in range(R):
+        c, k = 0.0, S - 1
+        cum = torch.cumsum(w[r, :, 0], 0)  # the same float32 running sum the renderer thresholds
+        for i in range(S):
+            if float(cum[i]) >= 0.5:
+                k = i
+                break
+        assert int(idx[r]) == k
+        assert float(depth[r]) == pytest.approx(float(starts[r, k] + starts[r, k + 1]) / 2, abs=1e-6)
