@@ -288,3 +288,25 @@ def test_eval_setup_rebuilds_a_run_folder_on_cpu(tmp_path):
     loaded.load_pipeline({("module." + k): v for k, v in extra.items()}, 12, strict=False)
     with pytest.raises(ValueError):
         loaded.load_pipeline({**extra, "_model.field.mlp_base.params": torch.zeros(4)}, 12, strict=False)
+
+
+def test_oracle_trainer_tool_runs_and_learns(tmp_path):
+    """tools/oracle_train.py (the CPU oracle trained with torch.optim.Adam: the reference-side run of DESIGN.md section 7): a few
+    iterations on a tiny scene lower the loss, the evaluation and the export + counting stages run."""
+    import importlib.util
+    import pathlib
+
+    path = pathlib.Path(__file__).resolve().parent.parent / "tools" / "oracle_train.py"
+    spec = importlib.util.spec_from_file_location("oracle_train_tool", path)
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    lines = []
+    res = tool.train(steps=6, seed=0, short_schedule=True, log_every=1, image_size=16, num_images=10, num_fruits=3, rays_per_batch=256,
+                     points_per_side=12, state_path=str(tmp_path / "state.pt"), do_export=True, log=lines.append)
+    h = res["history"]
+    assert [r["step"] for r in h] == [1, 2, 3, 4, 5, 6]
+    assert h[-1]["loss"] < h[0]["loss"] and all(math.isfinite(r["loss"]) for r in h)
+    assert {"rgb_loss", "semantics_loss", "interlevel_loss", "fields_grad_norm"} <= set(h[0])
+    assert set(res["eval"]) == {"psnr", "fruit_iou"} and math.isfinite(res["eval"]["psnr"])
+    assert res["export"]["export_points"] == 12 ** 3 and set(res["export"]["cloud_sizes"]) == {"semantic_colormap", "semantic", "density"}
+    assert (tmp_path / "state.pt").exists() and not res["events"]

@@ -183,7 +183,7 @@ def train(steps: int, seed: int, short_schedule: bool, log_every: int, method: s
         # AFTER_TRAIN_ITERATION: sampler.step_cb
         sampler_step = step
         since_update += 1
-        lv = float(loss)
+        lv = float(loss.detach())
         if not math.isfinite(lv):
             events.append({"step": step + 1, "event": "non-finite loss"})
             log(f"step {step + 1}: non-finite loss, stopping")
