@@ -33,6 +33,7 @@ class TrainerSpec:
     steps_per_save: int = 2000
     mixed_precision: bool = True
     description: str = ""
+    viewer_num_rays_per_chunk: int = 1 << 15  # ViewerConfig(num_rays_per_chunk=...): 1 << 13 for fruit_nerf (:57), 1 << 15 for big / huge (:107, :160)
 
 
 def _opt(kind: str, lr_final, max_steps):
@@ -49,6 +50,7 @@ fruit_nerf_method = TrainerSpec(
     ),
     optimizers={"proposal_networks": _opt("Adam", 1e-4, 200000), "fields": _opt("Adam", 1e-4, 200000)},
     description="Base config for FruitNeRF",
+    viewer_num_rays_per_chunk=1 << 13,
 )
 
 _big_model = dict(
@@ -121,7 +123,7 @@ def method_specification(spec: TrainerSpec):
         mixed_precision=spec.mixed_precision,
         pipeline=spec.pipeline,
         optimizers=optimizers,
-        viewer=ViewerConfig(num_rays_per_chunk=1 << 15),
+        viewer=ViewerConfig(num_rays_per_chunk=spec.viewer_num_rays_per_chunk),
         vis="viewer",
     )
     return MethodSpecification(config=config, description=spec.description)

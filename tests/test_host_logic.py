@@ -74,6 +74,86 @@ def test_method_configs_carry_reference_hyperparameters():
     assert FruitNerfModel is FruitModel
 
 
+def test_method_specification_against_a_stand_in_nerfstudio(monkeypatch):
+    """The ``MethodSpecification`` branch of fruit_nerf_config (taken when nerfstudio is importable, which it is not in this
+    image): run it against stand-in modules with the constructor signatures of nerfstudio 0.3.2's config classes and check
+    every value the reference sets (fruit_nerf/fruit_nerf_config.py:27-61, 63-111, 113-164)."""
+    import sys
+    import types
+    from dataclasses import dataclass, field as dfield
+    from typing import Any, Dict, Optional
+
+    from fruitnerf_b200 import fruit_nerf_config as fc
+
+    @dataclass
+    class ViewerConfig:
+        num_rays_per_chunk: int = 32768
+
+    @dataclass
+    class AdamOptimizerConfig:
+        lr: float = 0.0005
+        eps: float = 1e-08
+        weight_decay: float = 0
+
+    @dataclass
+    class RAdamOptimizerConfig(AdamOptimizerConfig):
+        pass
+
+    @dataclass
+    class ExponentialDecaySchedulerConfig:
+        lr_final: float = 0.000005
+        max_steps: int = 100000
+
+    @dataclass
+    class TrainerConfig:
+        method_name: Optional[str] = None
+        steps_per_eval_batch: int = 500
+        steps_per_save: int = 1000
+        max_num_iterations: int = 1000000
+        mixed_precision: bool = False
+        pipeline: Any = None
+        optimizers: Dict[str, Any] = dfield(default_factory=dict)
+        viewer: Any = None
+        vis: str = "wandb"
+
+    @dataclass
+    class MethodSpecification:
+        config: Any
+        description: str
+
+    tree = {
+        "nerfstudio": {}, "nerfstudio.configs": {}, "nerfstudio.engine": {}, "nerfstudio.plugins": {},
+        "nerfstudio.configs.base_config": {"ViewerConfig": ViewerConfig},
+        "nerfstudio.engine.optimizers": {"AdamOptimizerConfig": AdamOptimizerConfig, "RAdamOptimizerConfig": RAdamOptimizerConfig},
+        "nerfstudio.engine.schedulers": {"ExponentialDecaySchedulerConfig": ExponentialDecaySchedulerConfig},
+        "nerfstudio.engine.trainer": {"TrainerConfig": TrainerConfig},
+        "nerfstudio.plugins.types": {"MethodSpecification": MethodSpecification},
+    }
+    for name, attrs in tree.items():
+        mod = types.ModuleType(name)
+        mod.__dict__.update(attrs)
+        monkeypatch.setitem(sys.modules, name, mod)
+
+    want = {"fruit_nerf": (30000, 1 << 13, AdamOptimizerConfig, 200000, 200000), "fruit_nerf_big": (100000, 1 << 15, RAdamOptimizerConfig, None, 50000),
+            "fruit_nerf_huge": (100000, 1 << 15, RAdamOptimizerConfig, None, 50000)}
+    for name, (iters, chunk, opt_cls, prop_steps, field_steps) in want.items():
+        ms = fc.method_specification(fc.METHODS[name])
+        assert isinstance(ms, MethodSpecification) and ms.description.startswith("Base config for FruitNeRF")
+        c = ms.config
+        assert (c.method_name, c.max_num_iterations, c.steps_per_eval_batch, c.steps_per_save, c.mixed_precision, c.vis) == (
+            name, iters, 500, 2000, True, "viewer")
+        assert c.viewer.num_rays_per_chunk == chunk
+        assert c.pipeline is fc.METHODS[name].pipeline and c.pipeline._target.__name__ == "FruitPipeline"
+        assert set(c.optimizers) == {"proposal_networks", "fields"}
+        for group, steps in (("proposal_networks", prop_steps), ("fields", field_steps)):
+            o = c.optimizers[group]
+            assert type(o["optimizer"]) is opt_cls and o["optimizer"].lr == 1e-2 and o["optimizer"].eps == 1e-15
+            if steps is None:
+                assert o["scheduler"] is None  # fruit_nerf_config.py:90-94, 140-144: no scheduler on the proposal group
+            else:
+                assert o["scheduler"].lr_final == 1e-4 and o["scheduler"].max_steps == steps
+
+
 def test_model_requires_semantics_metadata_and_builds():
     cfg = FruitNerfModelConfig()
     sem = Semantics(filenames=[], classes=["fruit"], colors=torch.tensor([[0.0, 0, 0], [1.0, 0, 0]]))
