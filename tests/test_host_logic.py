@@ -306,3 +306,22 @@ def test_flat_gradient_allreduce_world2_gloo(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=120)
         assert p.returncode == 0, out
+
+
+def test_bf16_hi_lo_split_error_model():
+    """The numerical contract bench.py states in ``dtype``: the tensor-core MLPs multiply fp32 values as bf16 hi/lo pairs
+    (x = hi + lo, hi = bf16(x), lo = bf16(x - hi)) with three MMAs per product (hi*hi + lo*hi + hi*lo, fp32 accumulate; the lo*lo
+    term is dropped).  Emulated here in torch: the result stays within ~2^-16 of the exact product relative to sum |a||b| -- two
+    orders of magnitude inside the 1e-3 parity bar, and ~250x tighter than a single bf16 MMA."""
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(256, 64, generator=g)
+    b = torch.randn(64, 48, generator=g) * 0.3
+    split = lambda x: (x.bfloat16().float(), (x - x.bfloat16().float()).bfloat16().float())  # noqa: E731
+    (ah, al), (bh, bl) = split(a), split(b)
+    got = ah @ bh + al @ bh + ah @ bl
+    exact = a.double() @ b.double()
+    scale = a.abs().double() @ b.abs().double()
+    err3 = float(((got.double() - exact).abs() / scale).max())
+    err1 = float((((ah @ bh).double() - exact).abs() / scale).max())
+    assert err3 < 2.0 ** -15, err3
+    assert err1 > 50 * err3  # what a plain bf16 product would cost
