@@ -133,13 +133,17 @@ def export_and_count(fparams, spec, dm, points_per_side: int = 256, half_extent:
 
 
 def train(steps: int, seed: int, short_schedule: bool, log_every: int, method: str = "fruit_nerf", image_size: int = 160, num_images: int = 40,
-          num_fruits: int = 12, rays_per_batch=None, points_per_side: int = 256, state_path=None, do_export: bool = True, log=print):
+          num_fruits: int = 12, rays_per_batch=None, points_per_side: int = 256, state_path=None, do_export: bool = True, log=print, stream: int = 0):
     torch.manual_seed(seed)
     tspec = synthetic_spec(method, num_images, image_size, num_fruits, seed, rays_per_batch=rays_per_batch,
                            schedule_steps=steps if short_schedule else None)
     pipeline = tspec.pipeline.setup(device="cpu", test_mode="val")
     pipeline.train()
     model, dm, cfg = pipeline.model, pipeline.datamanager, pipeline.model.config
+    if stream:
+        # same scene and same initial parameters, a different stream of pixel batches and sampler jitter: run-to-run variance
+        torch.manual_seed(seed * 1000003 + stream)
+        dm._generator().manual_seed(seed * 7919 + 104729 * stream)
     fparams, spec, pparams, pspecs = _param_dicts(model)
     groups = model.get_param_groups()
     opts, scheds = {}, {}
@@ -201,7 +205,7 @@ def train(steps: int, seed: int, short_schedule: bool, log_every: int, method: s
                 torch.save({"step": step + 1, "pipeline": pipeline.state_dict()}, state_path)
     train_s = time.time() - t_start
     res = {"what": "CPU oracle (oracle/fruit_ref.py + oracle/ns_torch.py) trained with torch.optim.Adam; mirrors fruitnerf_b200.scripts.train",
-           "method": method, "steps": steps, "seed": seed, "lr_schedule": "1e-2 -> 1e-4 over the run" if short_schedule else "stock (200k steps)",
+           "method": method, "steps": steps, "seed": seed, "stream": stream, "lr_schedule": "1e-2 -> 1e-4 over the run" if short_schedule else "stock (200k steps)",
            "rays_per_batch": R, "threads": torch.get_num_threads(), "train_seconds": train_s, "train_rays_per_s": len(history) and history[-1]["step"] * R / train_s,
            "history": history, "events": events, "scene": {"images": num_images, "size": image_size, "fruits": num_fruits}}
     pipeline.eval()
@@ -226,13 +230,14 @@ def main(argv=None):
     ap.add_argument("--rays-per-batch", type=int, default=None)
     ap.add_argument("--points-per-side", type=int, default=256)
     ap.add_argument("--no-export", action="store_true")
+    ap.add_argument("--stream", type=int, default=0, help="non-zero: same scene / initial parameters, another stream of batches and jitter")
     ap.add_argument("--state", default=None, help="path of a periodically rewritten pipeline state dict")
     ap.add_argument("--json", default=None)
     a = ap.parse_args(argv)
     if a.threads:
         torch.set_num_threads(a.threads)
     res = train(a.steps, a.seed, not a.stock_schedule, a.log_every, image_size=a.image_size, num_images=a.num_images, num_fruits=a.num_fruits,
-                rays_per_batch=a.rays_per_batch, points_per_side=a.points_per_side, state_path=a.state, do_export=not a.no_export)
+                rays_per_batch=a.rays_per_batch, points_per_side=a.points_per_side, state_path=a.state, do_export=not a.no_export, stream=a.stream)
     if a.json:
         os.makedirs(os.path.dirname(a.json) or ".", exist_ok=True)
         with open(a.json, "w") as f:
